@@ -1,0 +1,147 @@
+"""Sentence -> index mapping, chunking and step batching.
+
+Reference components C4 (MLLIB:335-345: drop OOV words, split into chunks of
+at most ``maxSentenceLength`` words) and the outer loop of C7 (MLLIB:401-419).
+The reference batches at most ``batchSize`` (50) centres of ONE sentence per
+RPC; the B200 engine packs many whole sentences into one device step and keeps
+sentence boundaries as a per-token sentence id so windows never cross them
+(SURVEY.md Q3).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Iterator, List, Sequence, Tuple
+
+import numpy as np
+
+from .vocab import Vocabulary
+
+
+def java_split(line: str, sep: str = " ") -> List[str]:
+    """``String.split(" ")`` of the JVM: interior/leading empty tokens are kept,
+    trailing empty tokens are removed (SURVEY.md Q9 -- this is how the empty
+    string becomes a vocabulary word in the reference's test run, SPEC:85)."""
+    if line == "":
+        return [""]                 # Java: no match -> the input string itself
+    parts = line.split(sep)
+    while parts and parts[-1] == "":
+        parts.pop()
+    return parts
+
+
+@dataclass
+class EncodedCorpus:
+    """Flat int32 token stream plus sentence offsets (CSR)."""
+    tokens: np.ndarray          # int32 [N]
+    offsets: np.ndarray         # int64 [num_sentences + 1]
+
+    @property
+    def num_tokens(self) -> int:
+        return int(self.tokens.shape[0])
+
+    @property
+    def num_sentences(self) -> int:
+        return int(self.offsets.shape[0] - 1)
+
+    def sentence(self, i: int) -> np.ndarray:
+        return self.tokens[self.offsets[i]:self.offsets[i + 1]]
+
+
+def encode_corpus(sentences: Iterable[Sequence[str]], vocab: Vocabulary,
+                  max_sentence_length: int = 1000, use_native: bool = True) -> EncodedCorpus:
+    """words -> vocabulary indices, OOV dropped, chunked (MLLIB:335-343)."""
+    if use_native:
+        try:
+            from ..ops import host as _host
+            if _host.available() and isinstance(vocab.index, dict):
+                return _host.encode_corpus(sentences, vocab, max_sentence_length)
+        except Exception:  # pragma: no cover
+            pass
+    get = vocab.index.get
+    toks: List[int] = []
+    offs: List[int] = [0]
+    for s in sentences:
+        idx = [i for i in (get(w) for w in s) if i is not None]
+        for lo in range(0, len(idx), max_sentence_length):
+            chunk = idx[lo:lo + max_sentence_length]
+            toks.extend(chunk)
+            offs.append(len(toks))
+    return EncodedCorpus(np.asarray(toks, dtype=np.int32), np.asarray(offs, dtype=np.int64))
+
+
+def chunk_encoded(tokens: np.ndarray, offsets: np.ndarray, max_sentence_length: int) -> EncodedCorpus:
+    """Re-chunk an already encoded corpus so that no sentence exceeds the limit."""
+    lens = np.diff(offsets)
+    if lens.size == 0 or lens.max() <= max_sentence_length:
+        return EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64))
+    new_offs = [0]
+    for a, b in zip(offsets[:-1], offsets[1:]):
+        for lo in range(int(a), int(b), max_sentence_length):
+            new_offs.append(min(lo + max_sentence_length, int(b)))
+    return EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(new_offs, np.int64))
+
+
+@dataclass
+class StepBatch:
+    """One device step: whole sentences, at most ``step_tokens`` tokens."""
+    tokens: np.ndarray      # int32 [T]
+    sent_id: np.ndarray     # int32 [T]  (monotone, relative to the step)
+    raw_pos0: int           # position of tokens[0] in the (iteration-local) raw stream
+    n_words: int            # == T (raw words consumed, for the LR schedule)
+
+
+def iter_steps(corpus: EncodedCorpus, step_tokens: int) -> Iterator[StepBatch]:
+    """Pack consecutive sentences into steps of <= ``step_tokens`` tokens.
+
+    A sentence longer than ``step_tokens`` is split (windows at the cut are
+    lost, exactly like the reference loses them at ``maxSentenceLength`` cuts).
+    """
+    offs = corpus.offsets
+    ns = corpus.num_sentences
+    s = 0
+    while s < ns:
+        start = int(offs[s])
+        # number of whole sentences that fit
+        e = int(np.searchsorted(offs, start + step_tokens, side="right")) - 1
+        if e <= s:                       # a single sentence larger than the step
+            end = min(int(offs[s + 1]), start + step_tokens)
+            toks = corpus.tokens[start:end]
+            sid = np.zeros(end - start, dtype=np.int32)
+            yield StepBatch(toks, sid, start, end - start)
+            if end == int(offs[s + 1]):
+                s += 1
+            else:                        # leave the remainder as a shortened sentence
+                offs = offs.copy()
+                offs[s] = end
+            continue
+        end = int(offs[e])
+        toks = corpus.tokens[start:end]
+        lens = np.diff(offs[s:e + 1])
+        sid = np.repeat(np.arange(e - s, dtype=np.int32), lens)
+        yield StepBatch(toks, sid, start, end - start)
+        s = e
+
+
+def sentences_from_any(data, input_col: str | None = None) -> Iterable[Sequence[str]]:
+    """Adapter: pandas DataFrame / pyarrow Table / dict-of-columns /
+    list-of-lists / iterator -> iterable of token sequences.
+
+    This replaces ``dataset.select($(inputCol)).rdd.map(_.getAs[Seq[String]](0))``
+    (ML:286)."""
+    try:
+        import pandas as pd
+        if isinstance(data, pd.DataFrame):
+            if input_col is None or input_col not in data.columns:
+                raise ValueError(f"input column {input_col!r} not found in DataFrame")
+            return [list(x) if x is not None else [] for x in data[input_col].tolist()]
+    except ImportError:  # pragma: no cover
+        pass
+    try:
+        import pyarrow as pa
+        if isinstance(data, pa.Table):
+            return [list(x) if x is not None else [] for x in data.column(input_col).to_pylist()]
+    except ImportError:  # pragma: no cover
+        pass
+    if isinstance(data, dict):
+        return [list(x) for x in data[input_col]]
+    return data

@@ -1,0 +1,319 @@
+"""Per-rank shard engine: the B200 counterpart of a Glint parameter server.
+
+One ``ShardEngine`` lives in each process (one process per GPU).  It owns the
+rank's column slice of ``syn0`` (input vectors, "u") and ``syn1neg`` (output
+vectors, "v") for the FULL vocabulary plus the replicated noise tables, and
+implements every server-side operation the reference calls on
+``BigWord2VecMatrix``:
+
+====================  =========================================================
+reference (Glint) op  here
+====================  =========================================================
+``dotprod``+``adjust``  ``train_step`` (one fused sm_100a kernel incl. the
+                        cross-shard partial-dot all-reduce; CPU: torch ops +
+                        ``all_reduce``) -- MLLIB:421-425
+``pull``               ``pull``            -- MLLIB:514,539,639,652
+``pullAverage``        ``pull_average``    -- ML:453
+``norms``              ``norms``           -- MLLIB:486
+``multiply``           ``multiply`` / ``top_k`` (scores + cosine + top-k fused
+                        on device)         -- MLLIB:598-617
+``save`` / load        ``save_shard`` / ``load_columns``  -- MLLIB:494,722
+``destroy``            ``destroy``         -- MLLIB:665
+====================  =========================================================
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..data.sampler import AliasTable, keep_thresholds, unigram_alias
+from ..parallel.comm import Comm
+from ..parallel.sharding import ColumnShard, make_shard
+from ..utils import philox
+from . import sgns
+from .sgns import SGNSConfig
+
+
+@dataclass
+class EngineOptions:
+    """Engine knobs carried by ``parameterServerConfig``."""
+    batch_size: int = 50            # centres per mini-batch (reference ``batchSize``)
+    step_tokens: int = 0            # tokens per device step (0 = auto)
+    subsample_ratio: float = 1e-6
+    subsample_mode: str = "word2vec"    # "word2vec" | "reference" (Q1: inert)
+    transport: str = "auto"         # auto | p2p | nvls | nccl | gloo
+    concurrency: int = 0            # mini-batches in flight per step (0 = auto)
+    deterministic: bool = False     # two-phase kernels (all dots, then all updates)
+    kernel: str = "auto"            # auto | fused | twophase
+    store_syn1: bool = True         # keep syn1neg in saves (retrainable)
+
+    @classmethod
+    def from_dict(cls, d: Optional[dict]):
+        d = dict(d or {})
+        known = {k: d[k] for k in list(d) if k in cls.__dataclass_fields__}
+        return cls(**known)
+
+
+class ShardEngine:
+    def __init__(self, cfg: SGNSConfig, comm: Optional[Comm] = None,
+                 device: Optional[torch.device] = None, options: Optional[EngineOptions] = None):
+        self.cfg = cfg
+        self.comm = comm if comm is not None else Comm()
+        self.opts = options if options is not None else EngineOptions()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device("cpu")
+        self.device = torch.device(device)
+        self.shard: ColumnShard = make_shard(cfg.vector_size, self.comm.world, self.comm.rank)
+        self.syn0: Optional[torch.Tensor] = None      # [V, K] fp32
+        self.syn1: Optional[torch.Tensor] = None
+        self.alias: Optional[AliasTable] = None
+        self.keep_thresh: Optional[np.ndarray] = None
+        self._norms: Optional[torch.Tensor] = None
+        self._cuda = None
+        if self.device.type == "cuda":
+            from ..ops import cuda as _cuda_ops      # raises loudly if the extension is missing
+            self._cuda = _cuda_ops.CudaShardOps(self)
+
+    # ------------------------------------------------------------------ setup
+    @property
+    def is_cuda(self) -> bool:
+        return self.device.type == "cuda"
+
+    @property
+    def vocab_size(self) -> int:
+        return self.cfg.vocab_size
+
+    def init_weights(self, seed: Optional[int] = None):
+        """``syn0 ~ U(-0.5,0.5)/d`` on this shard's columns, ``syn1neg = 0``."""
+        seed = self.cfg.seed if seed is None else seed
+        sh = self.shard
+        v = self.cfg.vocab_size
+        if self.is_cuda:
+            self.syn0, self.syn1 = self._cuda.init_weights(seed)
+        else:
+            # scale uses the logical d; columns >= d are zero padding
+            full0, _ = sgns.init_embeddings(v, sh.padded_vector_size, seed, scale_dim=self.cfg.vector_size)
+            full0[:, self.cfg.vector_size:] = 0
+            self.syn0 = full0[:, sh.rank * sh.cols:(sh.rank + 1) * sh.cols].contiguous()
+            self.syn1 = torch.zeros(v, sh.cols, dtype=torch.float32)
+        self._norms = None
+
+    def set_noise(self, counts: np.ndarray, use_native: bool = True):
+        """Build the unigram^0.75 alias table and the sub-sampling thresholds
+        from the vocabulary counts (``bcVocabCns``, MLLIB:317,355)."""
+        counts = np.asarray(counts, dtype=np.int64)
+        if counts.shape[0] != self.cfg.vocab_size:
+            raise ValueError("counts length != vocab size")
+        self.alias = unigram_alias(counts, 0.75, use_native=use_native)
+        self.keep_thresh = keep_thresholds(counts, self.opts.subsample_ratio, self.opts.subsample_mode)
+        if self.is_cuda:
+            self._cuda.upload_noise(self.alias, self.keep_thresh)
+
+    def set_weights(self, syn0_full: Optional[torch.Tensor], syn1_full: Optional[torch.Tensor] = None):
+        """Install this rank's column slice of full [V, d] matrices."""
+        sh = self.shard
+        v = self.cfg.vocab_size
+
+        def _slice(full):
+            out = torch.zeros(v, sh.cols, dtype=torch.float32)
+            if sh.real_cols > 0:
+                out[:, :sh.real_cols] = full[:, sh.col_start:sh.col_start + sh.real_cols].to(torch.float32)
+            return out.to(self.device)
+
+        if syn0_full is not None:
+            self.syn0 = _slice(syn0_full)
+        self.syn1 = _slice(syn1_full) if syn1_full is not None else \
+            torch.zeros(v, sh.cols, dtype=torch.float32, device=self.device)
+        self._norms = None
+
+    def destroy(self):
+        self.syn0 = self.syn1 = None
+        self._norms = None
+        if self._cuda is not None:
+            self._cuda.release()
+
+    # --------------------------------------------------------------- training
+    def train_step(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float):
+        """One device step over ``tokens`` (whole sentences).
+
+        Sub-sampling, windowing, negative sampling, partial dots, the
+        cross-shard all-reduce, sigmoid/LR and the row updates all happen here.
+        Returns a 4-vector ``[pairs, loss, max|dot|, kept_tokens]`` (a device
+        tensor on GPUs so the caller decides when to synchronise).
+        """
+        if self.alias is None:
+            raise RuntimeError("set_noise() must be called before training")
+        self._norms = None
+        if self.is_cuda:
+            return self._cuda.train_step(tokens, sent_id, raw_pos0, iteration, alpha)
+        return self._train_step_cpu(np.asarray(tokens, dtype=np.int32), np.asarray(sent_id, dtype=np.int32),
+                                    raw_pos0, iteration, alpha)
+
+    def _train_step_cpu(self, tokens, sent_id, raw_pos0, iteration, alpha):
+        cfg = self.cfg
+        keep = sgns.subsample_mask(tokens, self.keep_thresh, cfg.seed, iteration, raw_pos0)
+        tokens = tokens[keep]
+        sent_id = sent_id[keep]
+        t = tokens.shape[0]
+        pairs = 0
+        loss = 0.0
+        maxdot = 0.0
+        bs = max(1, self.opts.batch_size)
+        for lo in range(0, t, bs):
+            st = self._minibatch_cpu(tokens, sent_id, raw_pos0, iteration, alpha, lo, min(t, lo + bs))
+            pairs += st.pairs
+            loss += st.loss
+            maxdot = max(maxdot, st.max_abs_dot)
+        return torch.tensor([pairs, loss, maxdot, t], dtype=torch.float64)
+
+    # --- the unfused Glint-style API (dotprod / adjust), used on CPU and by the baseline
+    def partial_dots(self, w: torch.Tensor, c: torch.Tensor, ng: torch.Tensor) -> torch.Tensor:
+        """Partial dot products over this shard's columns: [P, 1+n]."""
+        u = self.syn0[w]
+        f = torch.empty(w.shape[0], 1 + ng.shape[1], dtype=torch.float32, device=self.device)
+        f[:, 0] = (u * self.syn1[c]).sum(-1)
+        f[:, 1:] = torch.einsum("pd,pnd->pn", u, self.syn1[ng])
+        return f
+
+    def adjust(self, w, c, ng, gplus, gminus):
+        """Row updates on this shard's columns from pre-update values."""
+        u = self.syn0[w]
+        vc = self.syn1[c]
+        vn = self.syn1[ng]
+        du = gplus[:, None] * vc + torch.einsum("pn,pnd->pd", gminus, vn)
+        self.syn1.index_add_(0, c, gplus[:, None] * u)
+        self.syn1.index_add_(0, ng.reshape(-1), (gminus[:, :, None] * u[:, None, :]).reshape(-1, u.shape[1]))
+        self.syn0.index_add_(0, w, du)
+
+    def _minibatch_cpu(self, tokens, sent_id, pos0, iteration, alpha, lo, hi) -> sgns.StepStats:
+        cfg = self.cfg
+        ci, cj, slot = sgns.enumerate_pairs(cfg, tokens, sent_id, pos0, iteration, lo, hi)
+        stats = sgns.StepStats(pairs=int(ci.shape[0]))
+        # every rank enumerates the same pairs, so an empty batch is empty everywhere
+        if ci.shape[0] == 0:
+            return stats
+        pos = np.uint64(pos0) + ci.astype(np.uint64)
+        neg = sgns.draw_negatives(cfg, self.alias, pos, slot, iteration)
+        tok = tokens.astype(np.int64)
+        w = torch.from_numpy(tok[ci])
+        c = torch.from_numpy(tok[cj])
+        ng = torch.from_numpy(neg.astype(np.int64))
+        f = self.partial_dots(w, c, ng)
+        f = self.comm.all_reduce_sum(f)                   # the Glint client-side aggregation
+        neg_mask = (ng != c[:, None]).to(torch.float32)
+        gplus = sgns.sigmoid_coeff(f[:, 0], 1.0, alpha, cfg.sigmoid_mode, cfg.max_grad)
+        gminus = sgns.sigmoid_coeff(f[:, 1:], 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * neg_mask
+        stats.loss = float(sgns.sgns_loss(f[:, 0], f[:, 1:], neg_mask))
+        stats.max_abs_dot = float(f.abs().max())
+        self.adjust(w, c, ng, gplus, gminus)
+        return stats
+
+    # -------------------------------------------------------------- inference
+    def pull(self, rows) -> torch.Tensor:
+        """Full [R, d] input vectors for ``rows`` (collective)."""
+        rows = torch.as_tensor(rows, dtype=torch.int64)
+        if self.is_cuda:
+            part = self._cuda.gather_rows(rows)
+        else:
+            part = self.syn0[rows]
+        full = self.comm.all_gather_cols(part)
+        return full[:, :self.cfg.vector_size]
+
+    def pull_average(self, rows_flat, offsets) -> torch.Tensor:
+        """Per-sentence mean of input vectors (empty sentence -> zeros), [S, d]."""
+        rows_flat = torch.as_tensor(rows_flat, dtype=torch.int64)
+        offsets = torch.as_tensor(offsets, dtype=torch.int64)
+        ns = offsets.shape[0] - 1
+        if self.is_cuda:
+            part = self._cuda.segment_mean_rows(rows_flat, offsets)
+        else:
+            part = torch.zeros(ns, self.shard.cols, dtype=torch.float32)
+            lens = (offsets[1:] - offsets[:-1])
+            if rows_flat.numel() > 0:
+                seg = torch.repeat_interleave(torch.arange(ns), lens)
+                part.index_add_(0, seg, self.syn0[rows_flat])
+            part = part / lens.clamp(min=1).to(torch.float32)[:, None]
+        full = self.comm.all_gather_cols(part)
+        return full[:, :self.cfg.vector_size]
+
+    def norms(self) -> torch.Tensor:
+        """Euclidean norm of every input vector, [V] (cached; collective)."""
+        if self._norms is None:
+            if self.is_cuda:
+                sq = self._cuda.row_sqnorm()
+            else:
+                sq = (self.syn0 * self.syn0).sum(-1)
+            sq = self.comm.all_reduce_sum(sq)
+            self._norms = sq.sqrt()
+        return self._norms
+
+    def multiply(self, q) -> torch.Tensor:
+        """``syn0 @ q`` for a full-length query vector, [V] (collective)."""
+        q = torch.as_tensor(q, dtype=torch.float32).reshape(1, -1)
+        return self._scores(q)[0]
+
+    def _query_slice(self, q: torch.Tensor) -> torch.Tensor:
+        sh = self.shard
+        out = torch.zeros(q.shape[0], sh.cols, dtype=torch.float32)
+        if sh.real_cols:
+            out[:, :sh.real_cols] = q[:, sh.col_start:sh.col_start + sh.real_cols]
+        return out.to(self.device)
+
+    def _scores(self, q: torch.Tensor) -> torch.Tensor:
+        qs = self._query_slice(q)
+        if self.is_cuda:
+            part = self._cuda.scores(qs)              # [Q, V]
+        else:
+            part = qs @ self.syn0.t()
+        return self.comm.all_reduce_sum(part)
+
+    def top_k(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Cosine top-k against all input vectors (MLLIB:589-617).
+
+        ``queries`` [Q, d] need not be normalised.  Zero-norm rows score 0.
+        Returns (indices [Q, k], similarities [Q, k]) on the CPU.
+        """
+        q = torch.as_tensor(queries, dtype=torch.float32).reshape(-1, self.cfg.vector_size)
+        qn = q.norm(dim=1, keepdim=True)
+        q = torch.where(qn > 0, q / qn.clamp(min=1e-30), q)       # snrm2 / sscal (MLLIB:593-595)
+        k = min(k, self.cfg.vocab_size)
+        norms = self.norms()
+        if self.is_cuda:
+            idx, sim = self._cuda.top_k(self._query_slice(q), norms, k)
+            return idx.cpu(), sim.cpu()
+        scores = self._scores(q)
+        inv = torch.where(norms > 0, 1.0 / norms.clamp(min=1e-30), torch.zeros_like(norms))
+        cos = scores * inv[None, :]
+        sim, idx = torch.topk(cos, k, dim=1)
+        return idx, sim
+
+    # ------------------------------------------------------------ persistence
+    def shard_arrays(self) -> Dict[str, np.ndarray]:
+        """This rank's real (un-padded) column slices as numpy arrays."""
+        sh = self.shard
+        out = {"syn0": self.syn0[:, :sh.real_cols].detach().cpu().numpy()}
+        if self.syn1 is not None and self.opts.store_syn1:
+            out["syn1"] = self.syn1[:, :sh.real_cols].detach().cpu().numpy()
+        return out
+
+    def load_columns(self, name: str, col_start: int, block: np.ndarray):
+        """Install saved columns ``[col_start, col_start + block.shape[1])`` of
+        matrix ``name`` -- only the part overlapping this shard is kept, which
+        is what makes loading with a different shard count work (Q12)."""
+        sh = self.shard
+        v = self.cfg.vocab_size
+        for attr in ("syn0", "syn1"):
+            if getattr(self, attr) is None:
+                setattr(self, attr, torch.zeros(v, sh.cols, dtype=torch.float32, device=self.device))
+        target = self.syn0 if name == "syn0" else self.syn1
+        lo = max(col_start, sh.col_start)
+        hi = min(col_start + block.shape[1], sh.col_start + sh.real_cols)
+        if hi > lo:
+            src = torch.from_numpy(np.array(block[:, lo - col_start:hi - col_start], dtype=np.float32, order="C"))
+            target[:, lo - sh.col_start:hi - sh.col_start] = src.to(self.device)
+        self._norms = None

@@ -1,0 +1,129 @@
+"""Training driver: the client side of the reference's hot loop (C7/C8).
+
+Reference: ``doFit`` iterates ``numIterations`` times over the cached
+sentences, decays alpha every >10 000 words and issues one ``dotprod`` +
+``adjust`` round trip per <=50-centre mini-batch (MLLIB:364-433).  Here every
+rank runs this same loop in lock-step (SPMD): the token stream is replicated
+(or regenerated) on every rank, one ``ShardEngine.train_step`` covers
+thousands of mini-batches, and alpha follows the closed form with true global
+progress.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from ..data.corpus import EncodedCorpus, iter_steps
+from . import sgns
+from .engine import ShardEngine
+
+log = logging.getLogger("glint_word2vec_b200.trainer")
+
+
+@dataclass
+class TrainReport:
+    iterations: int = 0
+    steps: int = 0
+    words: int = 0
+    pairs: int = 0
+    loss_per_pair: float = float("nan")
+    max_abs_dot: float = 0.0
+    seconds: float = 0.0
+    final_alpha: float = 0.0
+    history: List[dict] = field(default_factory=list)
+
+    @property
+    def pairs_per_sec(self) -> float:
+        return self.pairs / self.seconds if self.seconds > 0 else float("nan")
+
+
+def auto_step_tokens(engine: ShardEngine, corpus_tokens: int) -> int:
+    """Tokens per device step.
+
+    GPUs want enough mini-batches in flight to fill 148 SMs; tiny corpora want
+    few concurrent mini-batches so summed stale updates do not blow up (the
+    README's exploding-gradient warning, README.md:17-19).  Rule: at most 1/64
+    of an iteration per step, clamped to [batch_size, 256k]."""
+    opts = engine.opts
+    if opts.step_tokens > 0:
+        return opts.step_tokens
+    if not engine.is_cuda:
+        return max(opts.batch_size, min(1 << 16, corpus_tokens))
+    return int(max(opts.batch_size, min(1 << 18, max(corpus_tokens // 64, 1))))
+
+
+def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_iterations: int,
+          train_words: Optional[int] = None, log_every_words: int = 10000,
+          metrics_path: Optional[str] = None, checkpoint_fn: Optional[Callable[[int, int], None]] = None,
+          start_iteration: int = 0, start_step: int = 0) -> TrainReport:
+    """Run ``num_iterations`` passes; every rank calls this with the same corpus."""
+    rep = TrainReport()
+    n_tok = corpus.num_tokens
+    train_words = n_tok if train_words is None else train_words
+    total_words = num_iterations * train_words
+    step_tokens = auto_step_tokens(engine, n_tok)
+    t0 = time.time()
+    pending = []
+    last_log = 0
+    mf = open(metrics_path, "a") if (metrics_path and engine.comm.rank == 0) else None
+    alpha = learning_rate
+    for k in range(start_iteration, num_iterations):
+        words_prev = k * train_words
+        words_it = 0
+        for si, batch in enumerate(iter_steps(corpus, step_tokens)):
+            if k == start_iteration and si < start_step:
+                words_it += batch.n_words
+                continue
+            alpha = sgns.learning_rate(learning_rate, words_prev + words_it, total_words)
+            stats = engine.train_step(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
+            pending.append(stats)
+            words_it += batch.n_words
+            rep.steps += 1
+            if words_prev + words_it - last_log > log_every_words or len(pending) >= 64:
+                last_log = words_prev + words_it
+                _drain(pending, rep, alpha, words_prev + words_it, mf)
+            if checkpoint_fn is not None:
+                checkpoint_fn(k, si + 1)
+        rep.iterations += 1
+        rep.words += words_it
+    _drain(pending, rep, alpha, rep.words, mf)
+    if engine.is_cuda:
+        torch.cuda.synchronize(engine.device)
+    rep.seconds = time.time() - t0
+    rep.final_alpha = alpha
+    if mf:
+        mf.close()
+    return rep
+
+
+def _drain(pending, rep: TrainReport, alpha, words, mf):
+    if not pending:
+        return
+    st = torch.stack([p.to("cpu", torch.float64) if isinstance(p, torch.Tensor) else torch.tensor(p)
+                      for p in pending])
+    pending.clear()
+    pairs = int(st[:, 0].sum())
+    loss = float(st[:, 1].sum())
+    maxdot = float(st[:, 2].max())
+    tot_pairs = rep.pairs + pairs
+    if tot_pairs > 0:
+        prev = 0.0 if rep.pairs == 0 or rep.loss_per_pair != rep.loss_per_pair else rep.loss_per_pair * rep.pairs
+        rep.loss_per_pair = (prev + loss) / tot_pairs
+    rep.pairs = tot_pairs
+    rep.max_abs_dot = max(rep.max_abs_dot, maxdot)
+    rec = {"words": int(words), "alpha": float(alpha), "pairs": pairs,
+           "loss_per_pair": (loss / pairs) if pairs else None, "max_abs_dot": maxdot}
+    rep.history.append(rec)
+    # same probe the reference logs every 10k words: wordCount, alpha, a dot product (MLLIB:411-412)
+    log.info("wordCount = %d, alpha = %.6g, loss/pair = %s, max|f| = %.4g", words, alpha,
+             rec["loss_per_pair"], maxdot)
+    if mf:
+        mf.write(json.dumps(rec) + "\n")
+        mf.flush()

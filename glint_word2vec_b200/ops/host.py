@@ -1,0 +1,50 @@
+"""Loader for the native host library (``csrc/host/textproc.cpp``).
+
+Vocabulary counting, corpus encoding and Vose alias construction are the
+reference's CPU-heavy cold-path pieces (Spark shuffle ``reduceByKey`` at
+MLLIB:262, the 1e8-entry unigram table of the Glint servers [G]); here they are
+C++ behind a pybind11 module built in-tree by ``build_ext.py``.  Pure-Python
+fallbacks exist in ``data/`` so the package works before the build.
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Iterable, Sequence
+
+import numpy as np
+
+_mod = None
+_tried = False
+
+
+def _load():
+    global _mod, _tried
+    if not _tried:
+        _tried = True
+        try:
+            _mod = importlib.import_module("glint_word2vec_b200._host")
+        except Exception:
+            _mod = None
+    return _mod
+
+
+def available() -> bool:
+    return _load() is not None
+
+
+def count_words(sentences: Iterable[Sequence[str]]):
+    m = _load()
+    return m.count_words(sentences)
+
+
+def encode_corpus(sentences, vocab, max_sentence_length: int):
+    from ..data.corpus import EncodedCorpus
+    m = _load()
+    toks, offs = m.encode_corpus(sentences, vocab.index, int(max_sentence_length))
+    return EncodedCorpus(np.asarray(toks, dtype=np.int32), np.asarray(offs, dtype=np.int64))
+
+
+def vose_alias(p: np.ndarray):
+    m = _load()
+    prob, alias = m.vose_alias(np.ascontiguousarray(p, dtype=np.float64))
+    return np.asarray(prob), np.asarray(alias)

@@ -1,0 +1,312 @@
+"""Shard-server group: the B200 counterpart of the Glint parameter-server cluster.
+
+Reference: parameter servers either run inside the Spark application
+("integrated", ``Client.runWithWord2VecMatrixOnSpark`` MLLIB:355) or as a
+separate long-lived application started with
+``spark-submit --class glint.Main ... spark [-c conf]`` whose master IP is then
+passed as ``parameterServerHost`` (README.md:52-57, MLLIB:358-360).
+
+Here a server group is S processes (one per GPU / column shard).  Rank 0 is the
+"master": it listens on a TCP port, receives requests from clients, broadcasts
+each request to the other ranks over the Gloo control group and all ranks
+execute it in lock-step on their shard; rank 0 returns the result.  Several
+matrices (models) can live on one group, like several ``BigWord2VecMatrix`` on
+one Glint cluster.
+
+Stand-alone ("separate") mode::
+
+    python -m glint_word2vec_b200.parallel.server --num-servers 8 --port 13380 [-c conf.json]
+
+prints ``master = <ip>:<port>`` -- pass it as ``parameterServerHost``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import os
+import socket
+import sys
+import time
+import traceback
+from multiprocessing.connection import Client as _ConnClient, Listener
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..data.corpus import EncodedCorpus
+from ..models import matrix_io, trainer
+from ..models.engine import EngineOptions, ShardEngine
+from ..models.sgns import SGNSConfig
+from .comm import Comm, TorchDistComm, init_process_group
+
+log = logging.getLogger("glint_word2vec_b200.server")
+
+DEFAULT_PORT = 13370           # cf. glint.master.port 13380 in separate-glint.conf (SEPCONF:3)
+AUTHKEY = b"glint-word2vec-b200"
+
+
+def parse_host(host: str, default_port: int = DEFAULT_PORT):
+    """``"ip"`` or ``"ip:port"`` -> (ip, port)."""
+    if ":" in host:
+        h, p = host.rsplit(":", 1)
+        return h, int(p)
+    return host, default_port
+
+
+def free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class ShardServer:
+    """Per-rank request executor.  Every handler runs on ALL ranks."""
+
+    def __init__(self, comm: Comm, device: torch.device, default_options: Optional[dict] = None):
+        self.comm = comm
+        self.device = device
+        self.default_options = dict(default_options or {})
+        self.engines: Dict[str, ShardEngine] = {}
+        self.reports: Dict[str, dict] = {}
+
+    # -- helpers
+    def _opts(self, opts: Optional[dict]) -> EngineOptions:
+        merged = dict(self.default_options)
+        merged.update(opts or {})
+        return EngineOptions.from_dict(merged)
+
+    def _eng(self, mid: str) -> ShardEngine:
+        if mid not in self.engines:
+            raise KeyError(f"no matrix {mid!r} on this server group (destroyed or never created)")
+        return self.engines[mid]
+
+    # -- handlers (names are the wire protocol)
+    def op_info(self):
+        return {"world": self.comm.world, "device": str(self.device),
+                "matrices": sorted(self.engines), "pid": os.getpid()}
+
+    def op_create(self, mid, cfg, opts, counts):
+        eng = ShardEngine(SGNSConfig(**cfg), comm=self.comm, device=self.device, options=self._opts(opts))
+        eng.init_weights()
+        eng.set_noise(np.asarray(counts))
+        self.engines[mid] = eng
+        return {"cols": eng.cfg.vector_size, "shards": self.comm.world}
+
+    def op_fit(self, mid, tokens, offsets, lr, iters, train_words, metrics_path=None):
+        eng = self._eng(mid)
+        corpus = EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64))
+        rep = trainer.train(eng, corpus, lr, iters, train_words, metrics_path=metrics_path)
+        out = {k: getattr(rep, k) for k in ("iterations", "steps", "words", "pairs", "loss_per_pair",
+                                             "max_abs_dot", "seconds", "final_alpha")}
+        out["history"] = rep.history[-50:]
+        self.reports[mid] = out
+        return out
+
+    def op_pull(self, mid, rows):
+        return self._eng(mid).pull(np.asarray(rows, np.int64)).cpu().numpy()
+
+    def op_pull_average(self, mid, rows_flat, offsets):
+        return self._eng(mid).pull_average(np.asarray(rows_flat, np.int64),
+                                           np.asarray(offsets, np.int64)).cpu().numpy()
+
+    def op_norms(self, mid):
+        return self._eng(mid).norms().cpu().numpy()
+
+    def op_multiply(self, mid, q):
+        return self._eng(mid).multiply(np.asarray(q, np.float32)).cpu().numpy()
+
+    def op_top_k(self, mid, queries, k):
+        idx, sim = self._eng(mid).top_k(np.asarray(queries, np.float32), int(k))
+        return idx.numpy(), sim.numpy()
+
+    def op_save(self, mid, path, extra=None):
+        matrix_io.save_matrix(self._eng(mid), path, extra)
+        return True
+
+    def op_load(self, mid, path, opts=None, with_syn1=True):
+        eng = matrix_io.load_matrix(path, self.comm, self.device, self._opts(opts), with_syn1)
+        self.engines[mid] = eng
+        return {"cols": eng.cfg.vector_size, "shards": self.comm.world,
+                "vocab_size": eng.cfg.vocab_size, "config": eng.cfg.to_dict()}
+
+    def op_set_noise(self, mid, counts):
+        self._eng(mid).set_noise(np.asarray(counts))
+        return True
+
+    def op_destroy(self, mid):
+        eng = self.engines.pop(mid, None)
+        if eng is not None:
+            eng.destroy()
+        return True
+
+    def execute(self, req: dict):
+        fn = getattr(self, "op_" + req["op"], None)
+        if fn is None:
+            raise ValueError(f"unknown op {req['op']!r}")
+        return fn(*req.get("args", ()), **req.get("kwargs", {}))
+
+
+def _bcast_request(comm: Comm, req):
+    """Rank 0 -> all ranks.  numpy payloads ride as pickled objects on the Gloo
+    control group (cold path; the hot path never leaves the device)."""
+    if comm.world == 1:
+        return req
+    return comm.broadcast_object(req, src=0)
+
+
+def serve(comm: Comm, device: torch.device, port: int, bind: str = "0.0.0.0",
+          options: Optional[dict] = None, ready_file: Optional[str] = None):
+    """Run the request loop until a ``shutdown`` request arrives."""
+    server = ShardServer(comm, device, options)
+    listener = None
+    if comm.rank == 0:
+        listener = Listener((bind, port), authkey=AUTHKEY)
+        ip = _local_ip()
+        # the reference prints the master IP to the log for the user to copy (README.md:56)
+        print(f"master = {ip}:{port}", flush=True)
+        if ready_file:
+            with open(ready_file, "w") as f:
+                json.dump({"host": ip, "port": port, "pid": os.getpid(), "world": comm.world}, f)
+    running = True
+    while running:
+        conn = None
+        if comm.rank == 0:
+            try:
+                conn = listener.accept()
+            except Exception as e:  # bad auth etc.
+                log.warning("rejected connection: %s", e)
+                continue
+        while True:
+            req = None
+            if comm.rank == 0:
+                try:
+                    req = conn.recv()
+                except (EOFError, ConnectionError, OSError):
+                    req = {"op": "_disconnect"}
+            req = _bcast_request(comm, req)
+            if req["op"] == "_disconnect":
+                break
+            if req["op"] == "shutdown":
+                running = False
+                if comm.rank == 0:
+                    try:
+                        conn.send({"ok": True, "result": True})
+                    except Exception:
+                        pass
+                break
+            try:
+                result = server.execute(req)
+                resp = {"ok": True, "result": result}
+            except Exception as e:
+                resp = {"ok": False, "error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()}
+            if comm.rank == 0:
+                try:
+                    conn.send(resp)
+                except (ConnectionError, OSError):
+                    pass
+        if conn is not None:
+            try:
+                conn.close()
+            except Exception:
+                pass
+    if listener is not None:
+        listener.close()
+    for mid in list(server.engines):
+        server.op_destroy(mid)
+
+
+def _local_ip() -> str:
+    try:
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        s.connect(("10.255.255.255", 1))
+        ip = s.getsockname()[0]
+        s.close()
+        return ip
+    except Exception:
+        return "127.0.0.1"
+
+
+def rank_main(rank: int, world: int, port: int, master_port: int, device_type: str,
+              options: Optional[dict], ready_file: Optional[str], bind: str = "0.0.0.0"):
+    """Entry point of one server rank (one process per GPU)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(master_port)
+    os.environ["RANK"] = str(rank)
+    os.environ["WORLD_SIZE"] = str(world)
+    os.environ["LOCAL_RANK"] = str(rank)
+    if device_type == "cuda":
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+    else:
+        device = torch.device("cpu")
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    comm: Comm
+    if world > 1:
+        init_process_group(rank=rank, world=world, master_port=master_port, device=device)
+        comm = TorchDistComm()
+    else:
+        comm = Comm()
+    try:
+        serve(comm, device, port, bind=bind, options=options, ready_file=ready_file)
+    finally:
+        if world > 1 and dist.is_initialized():
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="stand-alone shard-server group (cf. glint.Main)")
+    ap.add_argument("--num-servers", "-n", type=int, default=0, help="column shards (0 = all GPUs, or 1 on CPU)")
+    ap.add_argument("--port", type=int, default=DEFAULT_PORT)
+    ap.add_argument("--bind", default="0.0.0.0")
+    ap.add_argument("--device", default="auto", choices=["auto", "cuda", "cpu"])
+    ap.add_argument("-c", "--config", default=None, help="JSON file with engine options (cf. `-c separate-glint.conf`)")
+    ap.add_argument("--ready-file", default=None)
+    ap.add_argument("--rank", type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--master-port", type=int, default=None, help=argparse.SUPPRESS)
+    args = ap.parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    device_type = args.device
+    if device_type == "auto":
+        device_type = "cuda" if torch.cuda.is_available() else "cpu"
+    world = args.num_servers
+    if world <= 0:
+        world = torch.cuda.device_count() if device_type == "cuda" else 1
+    options = None
+    if args.config:
+        with open(args.config) as f:
+            options = json.load(f)
+        port = int(options.get("port", args.port)) if args.port == DEFAULT_PORT else args.port
+    else:
+        port = args.port
+    if args.rank is not None:                      # child rank
+        rank_main(args.rank, world, port, args.master_port, device_type, options, args.ready_file, args.bind)
+        return
+    master_port = free_port()
+    if world == 1:
+        rank_main(0, 1, port, master_port, device_type, options, args.ready_file, args.bind)
+        return
+    import subprocess
+    procs = []
+    for r in range(world):
+        cmd = [sys.executable, "-m", "glint_word2vec_b200.parallel.server", "--num-servers", str(world),
+               "--port", str(port), "--bind", args.bind, "--device", device_type, "--rank", str(r),
+               "--master-port", str(master_port)]
+        if args.config:
+            cmd += ["-c", args.config]
+        if args.ready_file:
+            cmd += ["--ready-file", args.ready_file]
+        procs.append(subprocess.Popen(cmd))
+    rc = 0
+    for p in procs:
+        rc = p.wait() or rc
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()
