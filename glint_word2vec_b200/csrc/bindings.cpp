@@ -1,0 +1,220 @@
+// torch <-> kernel glue.  Only this file sees torch headers; the kernels take
+// raw pointers + a stream (csrc/launchers.h, csrc/sgns_params.h).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+#include <vector>
+
+#include "launchers.h"
+#include "sgns_params.h"
+#include "nn_tc.h"
+
+namespace {
+
+using torch::Tensor;
+
+#define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+#define CHECK_CONTIG(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define CHECK_DT(x, dt) TORCH_CHECK((x).scalar_type() == dt, #x " has wrong dtype")
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e));
+}
+
+void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n_tokens, Tensor alias,
+               Tensor stats, int64_t pos0, int64_t seed, int64_t iteration, int64_t window, int64_t negatives,
+               int64_t window_mode, double alpha, double max_grad, bool compute_loss, int64_t grid,
+               int64_t world, int64_t rank, int64_t tile_centers, int64_t slot_floats,
+               std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs, int64_t xbuf_mc,
+               c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing) {
+    CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
+    CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
+    CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
+    CHECK_DT(alias, torch::kInt32); CHECK_DT(stats, torch::kFloat32);
+    TORCH_CHECK(syn0.size(1) % 4 == 0, "row stride must be a multiple of 4 floats");
+    TORCH_CHECK(syn0.size(1) <= 1024, "at most 1024 columns per shard are supported");
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::SgnsParams p{};
+    p.syn0 = syn0.data_ptr<float>();
+    p.syn1 = syn1.data_ptr<float>();
+    p.tokens = tokens.data_ptr<int>();
+    p.sent_id = sent_id.data_ptr<int>();
+    p.n_tokens = n_tokens.data_ptr<int>();
+    p.alias = reinterpret_cast<const int2*>(alias.data_ptr<int>());
+    p.stats = stats.data_ptr<float>();
+    p.pos0 = (unsigned long long)pos0;
+    p.seed_lo = (uint32_t)((uint64_t)seed & 0xFFFFFFFFull);
+    p.seed_hi = (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull);
+    p.iteration = (uint32_t)iteration;
+    p.vocab = (int)syn0.size(0);
+    p.K = (int)syn0.size(1);
+    p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
+    p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
+    p.world = (int)world; p.rank = (int)rank;
+    p.tile_centers = (int)tile_centers; p.slot_floats = (int)slot_floats;
+    if (world > 1) {
+        TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
+        TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
+        TORCH_CHECK(cta_seq.has_value() && error_flag.has_value(), "cta_seq/error_flag required");
+        TORCH_CHECK(tile_centers >= 1 && tile_centers <= 256, "tile_centers must be in [1, 256]");
+        for (int r = 0; r < world; ++r) {
+            p.xbuf[r] = reinterpret_cast<float*>(xbuf_ptrs[r]);
+            p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+        }
+        p.xbuf_mc = reinterpret_cast<float*>(xbuf_mc);
+        p.cta_seq = reinterpret_cast<uint32_t*>(cta_seq->data_ptr<int>());
+        p.error_flag = error_flag->data_ptr<int>();
+        p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
+        gw2v::launch_sgns_multi(p, (int)grid, cur_stream());
+    } else {
+        gw2v::launch_sgns_single(p, (int)grid, cur_stream());
+    }
+    check_launch("sgns_step");
+}
+
+int64_t sgns_single_grid(int64_t K, int64_t device) { return gw2v::sgns_single_grid((int)K, (int)device); }
+int64_t sgns_multi_max_grid(int64_t K, int64_t window, int64_t negatives, int64_t tile_centers, int64_t device) {
+    c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+    return gw2v::sgns_multi_max_grid((int)K, (int)window, (int)negatives, (int)tile_centers, (int)device);
+}
+
+void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thresh, int64_t seed,
+                       int64_t iteration, int64_t raw_pos0, Tensor tok_out, Tensor sid_out, Tensor count_out,
+                       Tensor ticket, Tensor chain, int64_t epoch) {
+    CHECK_CUDA(tok_in); CHECK_DT(tok_in, torch::kInt32); CHECK_DT(sid_in, torch::kInt32);
+    CHECK_DT(keep_thresh, torch::kInt32); CHECK_DT(chain, torch::kInt64); CHECK_DT(ticket, torch::kInt32);
+    TORCH_CHECK(chain.numel() >= gw2v::subsample_max_blocks((int)T), "chain buffer too small");
+    TORCH_CHECK(tok_out.numel() >= T && sid_out.numel() >= T, "output buffers too small");
+    c10::cuda::CUDAGuard guard(tok_in.device());
+    gw2v::launch_subsample_compact(
+        tok_in.data_ptr<int>(), sid_in.data_ptr<int>(), (int)T,
+        reinterpret_cast<const uint32_t*>(keep_thresh.data_ptr<int>()),
+        (uint32_t)((uint64_t)seed & 0xFFFFFFFFull), (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull),
+        (uint32_t)iteration, (unsigned long long)raw_pos0, tok_out.data_ptr<int>(), sid_out.data_ptr<int>(),
+        count_out.data_ptr<int>(), reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()),
+        reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch, cur_stream());
+    check_launch("subsample_compact");
+}
+
+int64_t subsample_max_blocks(int64_t max_tokens) { return gw2v::subsample_max_blocks((int)max_tokens); }
+
+void zipf_stream(Tensor alias, int64_t seed, int64_t pos0, Tensor out) {
+    CHECK_CUDA(alias); CHECK_DT(alias, torch::kInt32); CHECK_DT(out, torch::kInt32);
+    c10::cuda::CUDAGuard guard(alias.device());
+    gw2v::launch_zipf_stream(reinterpret_cast<const int2*>(alias.data_ptr<int>()), (int)alias.size(0),
+                             (uint32_t)((uint64_t)seed & 0xFFFFFFFFull),
+                             (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull), (unsigned long long)pos0,
+                             (int)out.numel(), out.data_ptr<int>(), cur_stream());
+    check_launch("zipf_stream");
+}
+
+void init_syn0(Tensor syn0, int64_t col_start, int64_t vector_size, int64_t seed) {
+    CHECK_CUDA(syn0); CHECK_CONTIG(syn0); CHECK_DT(syn0, torch::kFloat32);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::launch_init_syn0(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), (int)col_start,
+                           (int)vector_size, (uint32_t)((uint64_t)seed & 0xFFFFFFFFull),
+                           (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull), cur_stream());
+    check_launch("init_syn0");
+}
+
+Tensor gather_rows(Tensor syn0, Tensor rows) {
+    CHECK_CUDA(syn0); CHECK_CUDA(rows); CHECK_DT(rows, torch::kInt64); CHECK_CONTIG(syn0);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    auto out = torch::empty({rows.numel(), syn0.size(1)}, syn0.options());
+    gw2v::launch_gather_rows(syn0.data_ptr<float>(), reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()), (int)rows.numel(), (int)syn0.size(1),
+                             out.data_ptr<float>(), cur_stream());
+    check_launch("gather_rows");
+    return out;
+}
+
+Tensor segment_mean_rows(Tensor syn0, Tensor rows, Tensor offsets) {
+    CHECK_CUDA(syn0); CHECK_CUDA(rows); CHECK_CUDA(offsets); CHECK_DT(rows, torch::kInt64);
+    CHECK_DT(offsets, torch::kInt64);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    int64_t ns = offsets.numel() - 1;
+    auto out = torch::empty({ns, syn0.size(1)}, syn0.options());
+    gw2v::launch_segment_mean_rows(syn0.data_ptr<float>(), reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()), reinterpret_cast<const long long*>(offsets.data_ptr<int64_t>()),
+                                   (int)ns, (int)syn0.size(1), out.data_ptr<float>(), cur_stream());
+    check_launch("segment_mean_rows");
+    return out;
+}
+
+Tensor row_sqnorm(Tensor syn0) {
+    CHECK_CUDA(syn0); CHECK_CONTIG(syn0);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    auto out = torch::empty({syn0.size(0)}, syn0.options());
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    gw2v::launch_row_sqnorm(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), out.data_ptr<float>(), sms,
+                            cur_stream());
+    check_launch("row_sqnorm");
+    return out;
+}
+
+Tensor scores_rows(Tensor syn0, Tensor qs) {
+    CHECK_CUDA(syn0); CHECK_CUDA(qs); CHECK_CONTIG(syn0); CHECK_CONTIG(qs);
+    TORCH_CHECK(qs.size(1) == syn0.size(1), "query slice width != shard columns");
+    TORCH_CHECK(qs.size(0) * qs.size(1) * 4 <= 200 * 1024, "query batch too large for the CUDA-core path");
+    c10::cuda::CUDAGuard guard(syn0.device());
+    auto out = torch::empty({qs.size(0), syn0.size(0)}, syn0.options());
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    gw2v::launch_scores_rows(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), qs.data_ptr<float>(),
+                             (int)qs.size(0), out.data_ptr<float>(), sms, cur_stream());
+    check_launch("scores_rows");
+    return out;
+}
+
+std::vector<Tensor> cosine_topk(Tensor scores, Tensor norms, int64_t k) {
+    CHECK_CUDA(scores); CHECK_CUDA(norms); CHECK_CONTIG(scores); CHECK_CONTIG(norms);
+    c10::cuda::CUDAGuard guard(scores.device());
+    int64_t Q = scores.size(0), V = scores.size(1);
+    int nchunks = gw2v::topk_num_chunks(V);
+    auto cand_v = torch::empty({Q, (int64_t)nchunks * k}, scores.options());
+    auto cand_i = torch::empty({Q, (int64_t)nchunks * k}, scores.options().dtype(torch::kInt64));
+    auto out_v = torch::empty({Q, k}, scores.options());
+    auto out_i = torch::empty({Q, k}, scores.options().dtype(torch::kInt64));
+    gw2v::launch_cosine_topk(scores.data_ptr<float>(), norms.data_ptr<float>(), V, (int)Q, (int)k,
+                             cand_v.data_ptr<float>(), reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()), out_v.data_ptr<float>(),
+                             reinterpret_cast<long long*>(out_i.data_ptr<int64_t>()), cur_stream());
+    check_launch("cosine_topk");
+    return {out_i, out_v};
+}
+
+// tcgen05 nearest-neighbour scores: out[q, v] = sum_k bf16/tf32(syn0[v,k]) * q[q,k]
+Tensor scores_tc(Tensor syn0, Tensor qs) {
+    CHECK_CUDA(syn0); CHECK_CUDA(qs); CHECK_CONTIG(syn0); CHECK_CONTIG(qs);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    auto out = torch::empty({qs.size(0), syn0.size(0)}, syn0.options());
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    int rc = gw2v::launch_scores_tc(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), qs.data_ptr<float>(),
+                                    (int)qs.size(0), out.data_ptr<float>(), sms, cur_stream());
+    TORCH_CHECK(rc == 0, "scores_tc: unsupported shape (K must be a multiple of 32, Q <= 256)");
+    check_launch("scores_tc");
+    return out;
+}
+
+bool scores_tc_supported(int64_t K, int64_t Q) { return gw2v::scores_tc_supported((int)K, (int)Q); }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("sgns_step", &sgns_step);
+    m.def("sgns_single_grid", &sgns_single_grid);
+    m.def("sgns_multi_max_grid", &sgns_multi_max_grid);
+    m.def("sgns_multi_smem_bytes", [](int64_t w, int64_t n, int64_t tb) {
+        return (int64_t)gw2v::sgns_multi_smem_bytes((int)w, (int)n, (int)tb); });
+    m.def("subsample_compact", &subsample_compact);
+    m.def("subsample_max_blocks", &subsample_max_blocks);
+    m.def("zipf_stream", &zipf_stream);
+    m.def("init_syn0", &init_syn0);
+    m.def("gather_rows", &gather_rows);
+    m.def("segment_mean_rows", &segment_mean_rows);
+    m.def("row_sqnorm", &row_sqnorm);
+    m.def("scores_rows", &scores_rows);
+    m.def("cosine_topk", &cosine_topk);
+    m.def("scores_tc", &scores_tc);
+    m.def("scores_tc_supported", &scores_tc_supported);
+}

@@ -1,0 +1,31 @@
+// Host-callable launchers of the sm_100a kernels (no torch headers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gw2v {
+
+// prep_kernels.cu
+void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const uint32_t* keep_thresh,
+                              uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration,
+                              unsigned long long raw_pos0, int* tok_out, int* sid_out, int* count_out,
+                              unsigned int* ticket, unsigned long long* chain, uint32_t epoch,
+                              cudaStream_t stream);
+int subsample_max_blocks(int max_tokens);
+void launch_zipf_stream(const int2* alias, int vocab, uint32_t seed_lo, uint32_t seed_hi,
+                        unsigned long long pos0, int n, int* out, cudaStream_t stream);
+void launch_init_syn0(float* syn0, long long vocab, int K, int col_start, int vector_size, uint32_t seed_lo,
+                      uint32_t seed_hi, cudaStream_t stream);
+
+// infer_kernels.cu
+void launch_gather_rows(const float* syn0, const long long* rows, int R, int K, float* out, cudaStream_t s);
+void launch_segment_mean_rows(const float* syn0, const long long* rows, const long long* offsets, int NS, int K,
+                              float* out, cudaStream_t s);
+void launch_row_sqnorm(const float* syn0, long long V, int K, float* out, int sms, cudaStream_t s);
+void launch_scores_rows(const float* syn0, long long V, int K, const float* qs, int Q, float* out, int sms,
+                        cudaStream_t s);
+int topk_num_chunks(long long V);
+void launch_cosine_topk(const float* scores, const float* norms, long long V, int Q, int k, float* cand_v,
+                        long long* cand_i, float* out_v, long long* out_i, cudaStream_t s);
+
+}  // namespace gw2v

@@ -1,0 +1,219 @@
+"""CUDA (sm_100a) execution of the shard-engine operations.
+
+Everything here dispatches to the hand-written kernels in ``csrc/`` through the
+in-tree extension ``glint_word2vec_b200/_C.so``.  There is deliberately NO
+PyTorch fallback on a GPU: if the extension is missing we fail loudly so a
+silent eager path can never masquerade as the product.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..utils import philox
+
+try:
+    from .. import _C                      # built by glint_word2vec_b200/build_ext.py
+except ImportError as e:                  # pragma: no cover
+    raise ImportError(
+        "glint_word2vec_b200._C (the sm_100a kernel extension) is not built; run "
+        "`python -m glint_word2vec_b200.build_ext` (or __graft_entry__.build()). "
+        f"Original error: {e}") from e
+
+U32_MAX = 0xFFFFFFFF
+WINDOW_MODES = {"reference": 0, "word2vec_c": 1}
+
+
+def extension():
+    return _C
+
+
+class CudaShardOps:
+    """GPU state + kernels of one ``ShardEngine``."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.dev = engine.device
+        torch.cuda.set_device(self.dev)
+        self.cfg = engine.cfg
+        self.K = engine.shard.cols
+        self.world = engine.comm.world
+        self.rank = engine.comm.rank
+        self.alias_dev: Optional[torch.Tensor] = None
+        self.keep_dev: Optional[torch.Tensor] = None
+        self.subsample_active = True
+        self._cap = 0
+        self._epoch = 0
+        self._stats_ring = None
+        self._stats_i = 0
+        self._xchg = None
+        self.compute_loss = True
+        self.timing: Optional[torch.Tensor] = None
+        self.launches = 0                    # kernel launches issued by this object (bench bookkeeping)
+        self._count_val = -1
+        self._props = torch.cuda.get_device_properties(self.dev)
+
+    # ------------------------------------------------------------------ setup
+    def init_weights(self, seed: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        v = self.cfg.vocab_size
+        syn0 = torch.empty(v, self.K, dtype=torch.float32, device=self.dev)
+        _C.init_syn0(syn0, self.rank * self.K, self.cfg.vector_size, int(seed))
+        self.launches += 1
+        syn1 = torch.zeros(v, self.K, dtype=torch.float32, device=self.dev)
+        return syn0, syn1
+
+    def upload_noise(self, alias, keep_thresh: np.ndarray):
+        self.alias_dev = torch.from_numpy(alias.packed()).to(self.dev)
+        self.keep_dev = torch.from_numpy(keep_thresh.view(np.int32).copy()).to(self.dev)
+        self.subsample_active = bool((keep_thresh != U32_MAX).any())
+
+    def release(self):
+        self._xchg = None
+        self.alias_dev = self.keep_dev = None
+        self._cap = 0
+
+    def _ensure_capacity(self, t: int):
+        if t <= self._cap:
+            return
+        cap = max(t, 1024)
+        d = self.dev
+        self.tok_in = torch.empty(cap, dtype=torch.int32, device=d)
+        self.sid_in = torch.empty(cap, dtype=torch.int32, device=d)
+        self.tok_c = torch.empty(cap, dtype=torch.int32, device=d)
+        self.sid_c = torch.empty(cap, dtype=torch.int32, device=d)
+        self.count = torch.zeros(1, dtype=torch.int32, device=d)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=d)
+        self.chain = torch.zeros(int(_C.subsample_max_blocks(cap)) + 1, dtype=torch.int64, device=d)
+        self.pin_tok = torch.empty(cap, dtype=torch.int32).pin_memory()
+        self.pin_sid = torch.empty(cap, dtype=torch.int32).pin_memory()
+        self._stats_ring = torch.zeros(256, 4, dtype=torch.float32, device=d)
+        self._count_val = -1
+        self._cap = cap
+
+    # ------------------------------------------------------------------ cross-shard exchange
+    def _setup_exchange(self):
+        """Symmetric exchange slots + flags for the in-kernel all-reduce."""
+        from ..parallel.symm import alloc_symmetric
+        cfg = self.cfg
+        tb = int(os.environ.get("GW2V_TILE_CENTERS", "16"))
+        grid = int(_C.sgns_multi_max_grid(self.K, cfg.window, cfg.negatives, tb, self.dev.index or 0))
+        # all ranks must launch the identical grid (the flag protocol pairs CTA c with CTA c)
+        g = torch.tensor([grid], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(g, op=dist.ReduceOp.MIN, group=self.e.comm.group)
+        grid = int(g.item())
+        maxpairs = tb * 2 * cfg.window
+        slot_floats = (maxpairs * (1 + cfg.negatives) + 3) // 4 * 4
+        xbytes = grid * 2 * self.world * slot_floats * 4
+        fbytes = grid * self.world * 4
+        fbytes = (fbytes + 255) // 256 * 256
+        buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
+        self._xchg = {
+            "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats,
+            "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
+            "mc": buf.multicast_ptr,
+            "cta_seq": torch.zeros(grid, dtype=torch.int32, device=self.dev),
+            "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
+        }
+        self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
+
+    # ------------------------------------------------------------------ training
+    def stage_tokens(self, tokens, sent_id) -> int:
+        """Host -> device copy of one step's inputs through pinned memory."""
+        t = int(len(tokens))
+        self._ensure_capacity(t)
+        if isinstance(tokens, torch.Tensor) and tokens.is_pinned():
+            self.tok_in[:t].copy_(tokens, non_blocking=True)
+            self.sid_in[:t].copy_(sent_id, non_blocking=True)
+        else:
+            self.pin_tok[:t].copy_(torch.as_tensor(np.ascontiguousarray(tokens, dtype=np.int32)))
+            self.pin_sid[:t].copy_(torch.as_tensor(np.ascontiguousarray(sent_id, dtype=np.int32)))
+            self.tok_in[:t].copy_(self.pin_tok[:t], non_blocking=True)
+            self.sid_in[:t].copy_(self.pin_sid[:t], non_blocking=True)
+        return t
+
+    def train_step(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float) -> torch.Tensor:
+        t = self.stage_tokens(tokens, sent_id)
+        return self.train_step_staged(t, raw_pos0, iteration, alpha)
+
+    def train_step_staged(self, t: int, raw_pos0: int, iteration: int, alpha: float) -> torch.Tensor:
+        return self.train_step_device(self.tok_in, self.sid_in, t, raw_pos0, iteration, alpha)
+
+    def train_step_device(self, tok_dev: torch.Tensor, sid_dev: torch.Tensor, t: int, raw_pos0: int,
+                          iteration: int, alpha: float) -> torch.Tensor:
+        """One step on tokens that already live on the device (int32 tensors of length >= t)."""
+        cfg = self.cfg
+        e = self.e
+        self._ensure_capacity(t)
+        if self.world > 1 and self._xchg is None:
+            self._setup_exchange()
+        if self.subsample_active:
+            self._epoch += 1
+            _C.subsample_compact(tok_dev, sid_dev, t, self.keep_dev, int(cfg.seed), int(iteration),
+                                 int(raw_pos0), self.tok_c, self.sid_c, self.count, self.ticket, self.chain,
+                                 self._epoch)
+            self.launches += 1
+            self._count_val = -1
+            tok, sid = self.tok_c, self.sid_c
+        else:
+            if self._count_val != t:
+                self.count.fill_(t)
+                self._count_val = t
+            tok, sid = tok_dev, sid_dev
+        self._stats_i = (self._stats_i + 1) % self._stats_ring.shape[0]
+        stats = self._stats_ring[self._stats_i]
+        stats.zero_()
+        wm = WINDOW_MODES[cfg.window_mode]
+        if self.world > 1:
+            x = self._xchg
+            _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
+                         int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                         float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank, x["tb"],
+                         x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing)
+        else:
+            if not hasattr(self, "_grid1"):
+                self._grid1 = int(_C.sgns_single_grid(self.K, self.dev.index or 0))
+            _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
+                         int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                         float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
+                         None, None, None)
+        self.launches += 1
+        return stats
+
+    # ------------------------------------------------------------------ inference
+    def _rows_dev(self, rows: torch.Tensor) -> torch.Tensor:
+        return rows.to(self.dev, torch.int64).contiguous()
+
+    def gather_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        self.launches += 1
+        return _C.gather_rows(self.e.syn0, self._rows_dev(rows))
+
+    def segment_mean_rows(self, rows_flat: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        self.launches += 1
+        return _C.segment_mean_rows(self.e.syn0, self._rows_dev(rows_flat), self._rows_dev(offsets))
+
+    def row_sqnorm(self) -> torch.Tensor:
+        self.launches += 1
+        return _C.row_sqnorm(self.e.syn0)
+
+    def scores(self, qs: torch.Tensor) -> torch.Tensor:
+        """Partial scores [Q, V] of this shard's columns."""
+        qs = qs.contiguous()
+        self.launches += 1
+        if _C.scores_tc_supported(self.K, qs.shape[0]) and os.environ.get("GW2V_NN_TC", "1") == "1":
+            return _C.scores_tc(self.e.syn0, qs)
+        outs = []
+        maxq = max(1, (192 * 1024) // (self.K * 4))
+        for lo in range(0, qs.shape[0], maxq):
+            outs.append(_C.scores_rows(self.e.syn0, qs[lo:lo + maxq].contiguous()))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def top_k(self, qs: torch.Tensor, norms: torch.Tensor, k: int):
+        part = self.scores(qs)
+        full = self.e.comm.all_reduce_sum(part)
+        self.launches += 2
+        idx, sim = _C.cosine_topk(full, norms.contiguous(), int(k))
+        return idx, sim

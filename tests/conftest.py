@@ -1,0 +1,44 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CORPUS = "/root/reference/de_wikipedia_articles_country_capitals.txt"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
+
+
+@pytest.fixture(scope="session")
+def corpus_sentences():
+    """The reference's integration-test corpus (SPEC:22-36) when mounted, else a
+    synthetic corpus with planted country/capital structure."""
+    from glint_word2vec_b200.data.corpus import java_split
+    if os.path.exists(CORPUS):
+        with open(CORPUS, encoding="utf-8") as f:
+            lines = f.read().split("\n")
+        return [java_split(l) for l in lines]
+    return synthetic_capitals_corpus()
+
+
+def synthetic_capitals_corpus(n_sent=6000, seed=0):
+    import random
+    rng = random.Random(seed)
+    pairs = [("österreich", "wien"), ("deutschland", "berlin"), ("frankreich", "paris"),
+             ("spanien", "madrid"), ("finnland", "helsinki"), ("grossbritannien", "london")]
+    filler = [f"w{i}" for i in range(300)]
+    sents = []
+    for _ in range(n_sent):
+        c, k = rng.choice(pairs)
+        s = [rng.choice(filler) for _ in range(rng.randint(3, 12))]
+        s.insert(rng.randint(0, len(s)), c)
+        s.insert(rng.randint(0, len(s)), k)
+        s.insert(rng.randint(0, len(s)), "hauptstadt")
+        sents.append(s)
+    return sents

@@ -1,0 +1,201 @@
+"""GPU numerics: every sm_100a kernel against a plain PyTorch / numpy fp32
+reference of the same op (SURVEY.md 4.3 "GPU kernels" tier)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from glint_word2vec_b200.data.sampler import (build_alias, keep_thresholds, unigram_alias, zipf_counts,
+                                              zipf_tokens)
+from glint_word2vec_b200.models import sgns
+from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+from glint_word2vec_b200.models.sgns import SGNSConfig
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _C():
+    from glint_word2vec_b200.ops.cuda import extension
+    return extension()
+
+
+def test_extension_is_native():
+    _dev()
+    C = _C()
+    assert C.__file__.endswith(".so") and "glint_word2vec_b200" in C.__file__
+
+
+def test_zipf_stream_matches_numpy_philox():
+    dev = _dev()
+    counts = zipf_counts(5000, 10 ** 6)
+    alias = build_alias(counts.astype(np.float64))
+    ref = zipf_tokens(alias, 4096, seed=1234567890123, pos0=(1 << 33) + 5)
+    out = torch.empty(4096, dtype=torch.int32, device=dev)
+    _C().zipf_stream(torch.from_numpy(alias.packed()).to(dev), 1234567890123, (1 << 33) + 5, out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("world,rank,d", [(1, 0, 100), (2, 1, 100), (8, 7, 300)])
+def test_init_syn0_matches_oracle(world, rank, d):
+    dev = _dev()
+    from glint_word2vec_b200.parallel.sharding import make_shard
+    sh = make_shard(d, world, rank)
+    v = 777
+    syn0 = torch.empty(v, sh.cols, device=dev)
+    _C().init_syn0(syn0, rank * sh.cols, d, 42)
+    full, _ = sgns.init_embeddings(v, sh.padded_vector_size, 42, scale_dim=d)
+    full[:, d:] = 0
+    ref = full[:, rank * sh.cols:(rank + 1) * sh.cols]
+    assert torch.equal(syn0.cpu(), ref)
+
+
+def test_subsample_compact_matches_numpy():
+    dev = _dev()
+    C = _C()
+    v = 2000
+    counts = zipf_counts(v, 10 ** 6)
+    keep = keep_thresholds(counts, 1e-3, "word2vec")
+    alias = build_alias(counts.astype(np.float64))
+    for t in (1, 777, 2048, 50000):
+        tokens = zipf_tokens(alias, t, seed=3)
+        sid = (np.arange(t) // 17).astype(np.int32)
+        mask = sgns.subsample_mask(tokens, keep, seed=99, iteration=2, raw_pos0=1000)
+        tok_out = torch.zeros(t, dtype=torch.int32, device=dev)
+        sid_out = torch.zeros(t, dtype=torch.int32, device=dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        chain = torch.zeros(int(C.subsample_max_blocks(t)) + 1, dtype=torch.int64, device=dev)
+        for epoch in (1, 2):      # second launch re-uses ticket/chain
+            C.subsample_compact(torch.from_numpy(tokens).to(dev), torch.from_numpy(sid).to(dev), t,
+                                torch.from_numpy(keep.view(np.int32).copy()).to(dev), 99, 2, 1000,
+                                tok_out, sid_out, count, ticket, chain, epoch)
+            n = int(count.item())
+            assert n == int(mask.sum())
+            assert np.array_equal(tok_out[:n].cpu().numpy(), tokens[mask])
+            assert np.array_equal(sid_out[:n].cpu().numpy(), sid[mask])
+
+
+def _make_engine(dev, v, d, window=5, n=5, window_mode="reference", seed=7):
+    cfg = SGNSConfig(v, d, window, n, seed=seed, window_mode=window_mode)
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng.init_weights()
+    counts = zipf_counts(v, 10 ** 7, 0.6)
+    eng.set_noise(counts)
+    return eng, counts
+
+
+@pytest.mark.parametrize("d,window,n,wmode", [(64, 5, 5, "reference"), (100, 5, 5, "reference"),
+                                              (128, 3, 7, "word2vec_c"), (512, 5, 5, "reference"),
+                                              (300, 5, 10, "word2vec_c"), (40, 5, 5, "reference")])
+def test_sgns_step_single_matches_oracle(d, window, n, wmode):
+    """Distinct centre/context tokens and V >> negatives: concurrent warps almost never
+    re-read a row another warp has just updated, so the Hogwild kernel must match the
+    summed mini-batch oracle closely (sequential-vs-batch oracle runs differ by < 1e-2 here)."""
+    dev = _dev()
+    v = 200000
+    eng, counts = _make_engine(dev, v, d, window, n, wmode)
+    g = torch.Generator().manual_seed(0)
+    syn1 = (torch.rand(v, eng.shard.cols, generator=g) - 0.5) * 0.5
+    syn1[:, d:] = 0
+    eng.syn1 = syn1.to(dev)
+    syn0 = eng.syn0.clone().cpu() * 20.0
+    eng.syn0 = syn0.to(dev)
+    t = 3000
+    rng = np.random.default_rng(1)
+    tokens = rng.choice(v, size=t, replace=False).astype(np.int32)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0[:, :d].clone(), syn1[:, :d].clone()
+    cfg = eng.cfg
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 12345, 1, 0.05)
+    stats = eng.train_step(tokens, sid, 12345, 1, 0.05).cpu()
+    assert int(stats[0]) == st.pairs
+    assert int(stats[3]) == t
+    assert abs(float(stats[1]) - st.loss) / st.loss < 2e-3
+    got0, got1 = eng.syn0.cpu()[:, :d], eng.syn1.cpu()[:, :d]
+    d0, d1 = got0 - syn0[:, :d], got1 - syn1[:, :d]
+    r0, r1 = ref0 - syn0[:, :d], ref1 - syn1[:, :d]
+    assert (r0.abs().sum() > 0) and (r1.abs().sum() > 0)
+    assert (d0 - r0).norm() / r0.norm() < 2e-2
+    assert (d1 - r1).norm() / r1.norm() < 5e-3
+    # padding columns never move
+    assert float(eng.syn0[:, d:].abs().sum()) == 0.0 or eng.shard.cols == d
+
+
+def test_sgns_step_hot_rows_hogwild_close():
+    """Dense collisions (tiny vocabulary): updates race by design; the result
+    must still be close to the summed mini-batch oracle and finite."""
+    dev = _dev()
+    v, d = 50, 64
+    eng, _ = _make_engine(dev, v, d)
+    t = 4000
+    rng = np.random.default_rng(2)
+    tokens = rng.integers(0, v, size=t).astype(np.int32)
+    sid = np.zeros(t, dtype=np.int32)
+    ref0, ref1 = eng.syn0.cpu().clone(), eng.syn1.cpu().clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, eng.cfg, eng.alias, tokens, sid, 0, 0, 0.01)
+    stats = eng.train_step(tokens, sid, 0, 0, 0.01).cpu()
+    assert int(stats[0]) == st.pairs
+    assert torch.isfinite(eng.syn0).all() and torch.isfinite(eng.syn1).all()
+    assert (eng.syn1.cpu() - ref1).norm() / ref1.norm() < 0.2
+
+
+def test_zero_pair_step_is_noop():
+    dev = _dev()
+    eng, _ = _make_engine(dev, 1000, 64)
+    before0, before1 = eng.syn0.clone(), eng.syn1.clone()
+    tokens = np.arange(10, dtype=np.int32)
+    sid = np.arange(10, dtype=np.int32)          # every token its own sentence -> no pairs
+    stats = eng.train_step(tokens, sid, 0, 0, 0.025).cpu()
+    assert int(stats[0]) == 0
+    assert torch.equal(eng.syn0, before0) and torch.equal(eng.syn1, before1)
+
+
+def test_inference_kernels_match_torch():
+    dev = _dev()
+    v, d = 30011, 100
+    eng, _ = _make_engine(dev, v, d)
+    eng.syn0 = (torch.randn(v, eng.shard.cols) * (torch.arange(eng.shard.cols) < d)).to(dev)
+    eng.syn0[5] = 0                                        # zero-norm row scores 0 (MLLIB:602-607)
+    full = eng.syn0.cpu()[:, :d]
+    rows = torch.tensor([0, 5, 17, v - 1, 17])
+    assert torch.equal(eng.pull(rows).cpu(), full[rows])
+    flat = torch.tensor([1, 2, 3, 10, 11, 7])
+    offs = torch.tensor([0, 3, 3, 5, 6])
+    avg = eng.pull_average(flat, offs).cpu()
+    ref = torch.stack([full[[1, 2, 3]].mean(0), torch.zeros(d), full[[10, 11]].mean(0), full[7]])
+    assert torch.allclose(avg, ref, atol=1e-6)
+    assert torch.allclose(eng.norms().cpu(), full.norm(dim=1), rtol=1e-5, atol=1e-6)
+    q = torch.randn(3, d)
+    sc = eng._scores(q).cpu()
+    assert torch.allclose(sc, q @ full.t(), rtol=1e-4, atol=1e-4)
+    idx, sim = eng.top_k(q, 12)
+    qn = q / q.norm(dim=1, keepdim=True)
+    nr = full.norm(dim=1)
+    cos = (qn @ full.t()) / torch.where(nr > 0, nr, torch.ones_like(nr))
+    cos[:, nr == 0] = 0
+    rs, ri = torch.topk(cos, 12, dim=1)
+    assert torch.allclose(sim, rs, rtol=1e-4, atol=1e-5)
+    assert (idx == ri).float().mean() > 0.95              # ties may permute
+
+
+def test_fit_on_gpu_golden(corpus_sentences):
+    """Scenario 1/10/12 of the reference spec on the device path (SPEC:83-106,290-352)."""
+    _dev()
+    from glint_word2vec_b200 import ServerSideGlintWord2Vec
+    est = ServerSideGlintWord2Vec(seed=1, stepSize=0.025, numPartitions=2, numParameterServers=1,
+                                  inputCol="sentence", outputCol="model", unigramTableSize=1000000,
+                                  parameterServerConfig={"subsample_mode": "reference", "step_tokens": 2000})
+    model = est.fit({"sentence": corpus_sentences})
+    try:
+        syn = model.findSynonymsArray("österreich", 10)
+        assert len(syn) == 10
+        words = [w for w, _ in syn]
+        assert "wien" in words
+        assert dict(syn)["wien"] > 0.9
+    finally:
+        model.stop()
