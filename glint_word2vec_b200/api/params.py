@@ -52,6 +52,14 @@ class Param:
         return isinstance(other, Param) and other.name == self.name
 
 
+def _gt0(v):
+    return v > 0
+
+
+def _ge0(v):
+    return v >= 0
+
+
 def _to_int(v):
     if isinstance(v, bool) or (isinstance(v, float) and int(v) != v):
         raise TypeError(f"Could not convert {v!r} to int")
@@ -301,18 +309,18 @@ class ServerSideGlintWord2VecBase(Params):
         # HasSeed default: this.getClass.getName.hashCode (Java String.hashCode)
         d("seed", "random seed.", default=java_string_hash(self._java_class), converter=_to_int)
         d("stepSize", "Step size to be used for each iteration of optimization (> 0).", 0.01875,
-          lambda v: v > 0, _to_float)
-        d("maxIter", "maximum number of iterations (>= 0).", 1, lambda v: v >= 0, _to_int)
+          _gt0, _to_float)
+        d("maxIter", "maximum number of iterations (>= 0).", 1, _ge0, _to_int)
         d("vectorSize", "the dimension of codes after transforming from words (> 0)", 100,
-          lambda v: v > 0, _to_int)
+          _gt0, _to_int)
         d("windowSize", "the window size (context words from [-window, window]) (> 0)", 5,
-          lambda v: v > 0, _to_int)
-        d("numPartitions", "number of partitions for sentences of words (> 0)", 1, lambda v: v > 0, _to_int)
+          _gt0, _to_int)
+        d("numPartitions", "number of partitions for sentences of words (> 0)", 1, _gt0, _to_int)
         d("minCount", "the minimum number of times a token must appear to be included in the "
-          "word2vec model's vocabulary (>= 0)", 5, lambda v: v >= 0, _to_int)
+          "word2vec model's vocabulary (>= 0)", 5, _ge0, _to_int)
         d("maxSentenceLength", "Maximum length (in words) of each sentence in the input data. Any sentence "
           "longer than this threshold will be divided into chunks up to the size (> 0)", 1000,
-          lambda v: v > 0, _to_int)
+          _gt0, _to_int)
         d("batchSize", "the mini batch size", 50, None, _to_int)
         d("n", "the number of random negative examples", 5, None, _to_int)
         d("subsampleRatio", "the ratio controlling how much subsampling occurs. "

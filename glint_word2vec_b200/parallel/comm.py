@@ -59,10 +59,11 @@ class TorchDistComm(Comm):
 
     def all_gather_cols(self, t):
         t = t.contiguous()
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        out = torch.empty((self.world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)
-        # [S, R, K] -> [R, S*K]
-        return out.permute(1, 0, 2).reshape(t.shape[0], self.world * t.shape[1])
+        # [S*R, K] -> [S, R, K] -> [R, S*K]
+        return out.view(self.world, t.shape[0], t.shape[1]).permute(1, 0, 2).reshape(
+            t.shape[0], self.world * t.shape[1])
 
     def broadcast_object(self, obj, src=0):
         lst = [obj]

@@ -1,0 +1,176 @@
+"""Oracle + distributed-CPU tiers: the column-sharded algebra must equal the dense
+single-process oracle (BASELINE.json config 1: vocab 10k, dim 64,
+neg 5, window 5 on CPU world_size=2 over Gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from glint_word2vec_b200.data.corpus import EncodedCorpus
+from glint_word2vec_b200.data.sampler import build_alias, zipf_counts, zipf_tokens
+from glint_word2vec_b200.models import matrix_io, sgns, trainer
+from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+from glint_word2vec_b200.models.sgns import SGNSConfig
+from glint_word2vec_b200.parallel.comm import Comm
+from glint_word2vec_b200.parallel.sharding import make_shard, shard_cols
+
+
+class FakeComm(Comm):
+    """A shard of a world whose collectives are driven by the test."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+
+def test_shard_layout():
+    assert shard_cols(512, 8) == 64 and shard_cols(300, 8) == 40 and shard_cols(100, 2) == 52
+    sh = [make_shard(300, 8, r) for r in range(8)]
+    assert sum(s.real_cols for s in sh) == 300 and sh[7].real_cols == 20 and sh[7].col_start == 280
+    assert all(s.cols % 4 == 0 for s in sh)
+    s5 = [make_shard(100, 5, r) for r in range(5)]                 # the reference default of 5 servers
+    assert [s.real_cols for s in s5] == [20] * 5
+
+
+def test_init_is_shard_invariant():
+    cfg = SGNSConfig(300, 100, seed=3)
+    full = ShardEngine(cfg, device=torch.device("cpu"))
+    full.init_weights()
+    parts = []
+    for r in range(3):
+        e = ShardEngine(cfg, comm=FakeComm(r, 3), device=torch.device("cpu"))
+        e.init_weights()
+        parts.append(e.syn0[:, :e.shard.real_cols])
+    assert torch.equal(torch.cat(parts, 1), full.syn0[:, :100])
+    assert float(full.syn0.abs().max()) <= 0.5 / 100 and float(full.syn1.abs().sum()) == 0.0
+
+
+def test_manual_two_shard_minibatch_equals_oracle():
+    """dotprod partials summed across shards + adjust per shard == dense oracle."""
+    v, d = 500, 64
+    cfg = SGNSConfig(v, d, 5, 5, seed=5)
+    counts = zipf_counts(v, 10 ** 5)
+    engines = [ShardEngine(cfg, comm=FakeComm(r, 2), device=torch.device("cpu")) for r in range(2)]
+    for e in engines:
+        e.init_weights()
+        e.set_noise(counts)
+        e.syn1 = torch.randn(v, e.shard.cols) * 0.1
+        e.syn0 = e.syn0 * 30
+    ref0 = torch.cat([e.syn0 for e in engines], 1).clone()
+    ref1 = torch.cat([e.syn1 for e in engines], 1).clone()
+    rng = np.random.default_rng(0)
+    tokens = rng.integers(0, v, 400).astype(np.int32)
+    sid = (np.arange(400) // 25).astype(np.int32)
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, engines[0].alias, tokens, sid, 77, 0, 0.05)
+    ci, cj, slot = sgns.enumerate_pairs(cfg, tokens, sid, 77, 0)
+    neg = sgns.draw_negatives(cfg, engines[0].alias, np.uint64(77) + ci.astype(np.uint64), slot, 0)
+    w = torch.from_numpy(tokens.astype(np.int64)[ci])
+    c = torch.from_numpy(tokens.astype(np.int64)[cj])
+    ng = torch.from_numpy(neg.astype(np.int64))
+    f = sum(e.partial_dots(w, c, ng) for e in engines)             # the all-reduce
+    mask = (ng != c[:, None]).float()
+    gp = sgns.sigmoid_coeff(f[:, 0], 1.0, 0.05)
+    gm = sgns.sigmoid_coeff(f[:, 1:], 0.0, 0.05) * mask
+    for e in engines:
+        e.adjust(w, c, ng, gp, gm)
+    got0 = torch.cat([e.syn0 for e in engines], 1)
+    got1 = torch.cat([e.syn1 for e in engines], 1)
+    assert st.pairs == w.shape[0] > 0
+    assert torch.allclose(got0, ref0, atol=1e-5) and torch.allclose(got1, ref1, atol=1e-5)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from glint_word2vec_b200.parallel.comm import TorchDistComm, init_process_group
+    torch.set_num_threads(2)
+    init_process_group("gloo", rank=rank, world=world, master_port=port)
+    try:
+        v, d = 10000, 64                                            # BASELINE.json config 1
+        cfg = SGNSConfig(v, d, 5, 5, seed=9)
+        counts = zipf_counts(v, 10 ** 6)
+        eng = ShardEngine(cfg, comm=TorchDistComm(), device=torch.device("cpu"),
+                          options=EngineOptions(batch_size=200, subsample_ratio=1e-3))
+        eng.init_weights()
+        eng.set_noise(counts)
+        alias = build_alias(counts.astype(np.float64))
+        toks = zipf_tokens(alias, 6000, seed=4)
+        corpus = EncodedCorpus(toks, np.arange(0, 6001, 40, dtype=np.int64))
+        rep = trainer.train(eng, corpus, 0.025, 2, train_words=6000)
+        vecs = eng.pull(torch.arange(v))
+        nrm = eng.norms()
+        idx, sim = eng.top_k(vecs[:3], 4)
+        avg = eng.pull_average(torch.tensor([1, 2, 3, 9]), torch.tensor([0, 3, 3, 4]))
+        matrix_io.save_matrix(eng, os.path.join(out_dir, "m2"))
+        if rank == 0:
+            torch.save({"vecs": vecs, "pairs": rep.pairs, "loss": rep.loss_per_pair, "nrm": nrm, "idx": idx,
+                        "sim": sim, "avg": avg}, os.path.join(out_dir, "r.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_equals_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_gloo_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r = torch.load(os.path.join(tmp_path, "r.pt"))
+    v, d = 10000, 64
+    cfg = SGNSConfig(v, d, 5, 5, seed=9)
+    counts = zipf_counts(v, 10 ** 6)
+    eng = ShardEngine(cfg, device=torch.device("cpu"), options=EngineOptions(batch_size=200, subsample_ratio=1e-3))
+    eng.init_weights()
+    eng.set_noise(counts)
+    toks = zipf_tokens(build_alias(counts.astype(np.float64)), 6000, seed=4)
+    rep = trainer.train(eng, EncodedCorpus(toks, np.arange(0, 6001, 40, dtype=np.int64)), 0.025, 2, train_words=6000)
+    vecs = eng.pull(torch.arange(v))
+    assert rep.pairs == r["pairs"] > 0
+    assert abs(rep.loss_per_pair - r["loss"]) < 1e-4
+    assert torch.allclose(vecs, r["vecs"], atol=1e-5)
+    assert torch.allclose(eng.norms(), r["nrm"], atol=1e-5)
+    assert r["idx"][:, 0].tolist() == [0, 1, 2]
+    ref_avg = torch.stack([vecs[[1, 2, 3]].mean(0), torch.zeros(d), vecs[9]])
+    assert torch.allclose(r["avg"], ref_avg, atol=1e-5)
+    # re-sharding on load (Q12): saved by 2 shards, loaded by 1 and by 3
+    one = matrix_io.load_matrix(os.path.join(tmp_path, "m2"), Comm(), torch.device("cpu"))
+    assert torch.allclose(one.syn0[:, :d], vecs, atol=1e-5)
+    parts = [matrix_io.load_matrix(os.path.join(tmp_path, "m2"), FakeComm(k, 3), torch.device("cpu")) for k in range(3)]
+    cat = torch.cat([p.syn0[:, :p.shard.real_cols] for p in parts], 1)
+    assert torch.allclose(cat, vecs, atol=1e-5)
+    meta = matrix_io.read_meta(os.path.join(tmp_path, "m2"))
+    assert meta["num_shards"] == 2 and [s["cols"] for s in meta["shards"]] == [32, 32]
+
+
+def test_training_reduces_loss_and_is_deterministic():
+    v, d = 2000, 32
+    counts = zipf_counts(v, 10 ** 5)
+    toks = zipf_tokens(build_alias(counts.astype(np.float64)), 20000, seed=1)
+    corpus = EncodedCorpus(toks, np.arange(0, 20001, 50, dtype=np.int64))
+
+    def run():
+        eng = ShardEngine(SGNSConfig(v, d, seed=2), device=torch.device("cpu"),
+                          options=EngineOptions(batch_size=100, subsample_ratio=1e-2))
+        eng.init_weights()
+        eng.set_noise(counts)
+        rep = trainer.train(eng, corpus, 0.05, 3, train_words=20000)
+        return eng, rep
+    e1, r1 = run()
+    e2, r2 = run()
+    assert torch.equal(e1.syn0, e2.syn0) and r1.pairs == r2.pairs
+    first, last = r1.history[0]["loss_per_pair"], r1.history[-1]["loss_per_pair"]
+    assert last < first < 6 * np.log(2) + 0.2
+    assert r1.final_alpha < 0.05 and r1.words == 3 * 20000
+
+
+def test_zero_iterations_leaves_random_init():
+    eng = ShardEngine(SGNSConfig(100, 16, seed=1), device=torch.device("cpu"))
+    eng.init_weights()
+    eng.set_noise(np.ones(100, dtype=np.int64))
+    before = eng.syn0.clone()
+    rep = trainer.train(eng, EncodedCorpus(np.arange(50, dtype=np.int32), np.array([0, 50])), 0.025, 0)   # Q8
+    assert rep.pairs == 0 and torch.equal(eng.syn0, before)

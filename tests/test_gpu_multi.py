@@ -1,0 +1,93 @@
+"""Multi-GPU: the in-kernel NVLink exchange of the fused SGNS step.
+
+World size 2/4/8 must reproduce the single-shard result (same Philox pairs and
+negatives; only fp32 summation order and Hogwild timing differ), and the
+serving collectives must match.  Skipped on boxes with fewer GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, d, out_dir):
+    import torch.distributed as dist
+    from glint_word2vec_b200.data.sampler import zipf_counts
+    from glint_word2vec_b200.models import sgns
+    from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+    from glint_word2vec_b200.models.sgns import SGNSConfig
+    from glint_word2vec_b200.parallel.comm import TorchDistComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        v, t = 100000, 6000
+        cfg = SGNSConfig(v, d, 5, 5, seed=11)
+        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference"))
+        eng.init_weights()
+        counts = zipf_counts(v, 10 ** 7, 0.6)
+        eng.set_noise(counts)
+        # non-trivial output vectors so dots/gradients are not all identical
+        full1 = (torch.rand(v, eng.shard.padded_vector_size, generator=torch.Generator().manual_seed(5)) - 0.5) * 0.5
+        full1[:, d:] = 0
+        eng.syn1 = full1[:, rank * eng.shard.cols:(rank + 1) * eng.shard.cols].contiguous().to(dev)
+        eng.syn0 = (eng.syn0 * 20.0).contiguous()
+        rng = np.random.default_rng(3)
+        steps = []
+        for s in range(3):
+            tokens = rng.choice(v, size=t, replace=False).astype(np.int32)
+            sid = (np.arange(t) // 41).astype(np.int32)
+            steps.append((tokens, sid))
+        start0 = eng.pull(torch.arange(v)).cpu()
+        stats = []
+        for s, (tokens, sid) in enumerate(steps):
+            stats.append(eng.train_step(tokens, sid, s * t, 0, 0.05).cpu())
+        torch.cuda.synchronize(dev)
+        got0 = eng.pull(torch.arange(v)).cpu()
+        nrm = eng.norms().cpu()
+        idx, sim = eng.top_k(got0[:4], 5)
+        if rank == 0:
+            # oracle: dense single-process mini-batch semantics, one mini-batch per step
+            ref0, _ = sgns.init_embeddings(v, d, 11)
+            ref0 = ref0 * 20.0
+            ref1 = full1[:, :d].clone()
+            assert torch.allclose(start0, ref0, atol=1e-7)
+            pairs = []
+            for s, (tokens, sid) in enumerate(steps):
+                st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, s * t, 0, 0.05)
+                pairs.append(st.pairs)
+            torch.save({"got0": got0, "ref0": ref0, "start0": start0, "pairs": pairs,
+                        "stats": torch.stack(stats), "nrm": nrm, "idx": idx, "sim": sim},
+                       os.path.join(out_dir, "result.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d", [(2, 128), (2, 100), (4, 256), (8, 512)])
+def test_fused_multi_matches_oracle(world, d, tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), d, str(tmp_path)), nprocs=world, join=True)
+    r = torch.load(os.path.join(tmp_path, "result.pt"))
+    assert [int(x) for x in r["stats"][:, 0]] == r["pairs"]
+    upd_ref = r["ref0"] - r["start0"]
+    upd_got = r["got0"] - r["start0"]
+    assert upd_ref.norm() > 0
+    assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2
+    assert torch.allclose(r["nrm"], r["got0"].norm(dim=1), rtol=1e-4, atol=1e-6)
+    # each of the first rows is its own nearest neighbour with cosine 1
+    assert r["idx"][:, 0].tolist() == [0, 1, 2, 3]
+    assert torch.allclose(r["sim"][:, 0], torch.ones(4), atol=1e-4)
