@@ -30,7 +30,8 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
                int64_t window_mode, double alpha, double max_grad, bool compute_loss, int64_t grid,
                int64_t world, int64_t rank, int64_t tile_centers, int64_t slot_floats,
                std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs, int64_t xbuf_mc,
-               c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing) {
+               c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing,
+               int64_t debug) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
     CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
@@ -54,6 +55,7 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
     p.K = (int)syn0.size(1);
     p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
     p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
+    p.debug = (int)debug;
     p.world = (int)world; p.rank = (int)rank;
     p.tile_centers = (int)tile_centers; p.slot_floats = (int)slot_floats;
     if (world > 1) {
@@ -187,11 +189,16 @@ std::vector<Tensor> cosine_topk(Tensor scores, Tensor norms, int64_t k) {
 Tensor scores_tc(Tensor syn0, Tensor qs) {
     CHECK_CUDA(syn0); CHECK_CUDA(qs); CHECK_CONTIG(syn0); CHECK_CONTIG(qs);
     c10::cuda::CUDAGuard guard(syn0.device());
+    TORCH_CHECK(qs.size(1) == syn0.size(1), "query slice width != shard columns");
+    TORCH_CHECK(gw2v::scores_tc_supported((int)syn0.size(1), (int)qs.size(0)), "scores_tc: unsupported shape");
     auto out = torch::empty({qs.size(0), syn0.size(0)}, syn0.options());
     int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-    int rc = gw2v::launch_scores_tc(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), qs.data_ptr<float>(),
+    int qp = gw2v::scores_tc_padded_queries((int)qs.size(0));
+    auto qpad = torch::zeros({qp, qs.size(1)}, qs.options());
+    qpad.narrow(0, 0, qs.size(0)).copy_(qs);
+    int rc = gw2v::launch_scores_tc(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), qpad.data_ptr<float>(),
                                     (int)qs.size(0), out.data_ptr<float>(), sms, cur_stream());
-    TORCH_CHECK(rc == 0, "scores_tc: unsupported shape (K must be a multiple of 32, Q <= 256)");
+    TORCH_CHECK(rc == 0, "scores_tc failed (rc=", rc, "): 1 = unsupported shape, 2 = TMA descriptor encode failed");
     check_launch("scores_tc");
     return out;
 }

@@ -23,6 +23,7 @@ struct SgnsParams {
     int window, negatives, window_mode;   // window_mode 0 = reference (Q2), 1 = word2vec.c
     float alpha, max_grad;
     int compute_loss;
+    int debug;                   // profiling only: bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads
     // ---- cross-shard exchange (world > 1)
     int world, rank;
     int tile_centers;            // centres per CTA tile

@@ -55,6 +55,7 @@ class CudaShardOps:
         self.timing: Optional[torch.Tensor] = None
         self.launches = 0                    # kernel launches issued by this object (bench bookkeeping)
         self._count_val = -1
+        self.debug = int(os.environ.get("GW2V_DEBUG", "0"))      # profiling-only kernel switches
         self._props = torch.cuda.get_device_properties(self.dev)
 
     # ------------------------------------------------------------------ setup
@@ -172,14 +173,15 @@ class CudaShardOps:
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank, x["tb"],
-                         x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing)
+                         x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing,
+                         self.debug)
         else:
             if not hasattr(self, "_grid1"):
                 self._grid1 = int(_C.sgns_single_grid(self.K, self.dev.index or 0))
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
-                         None, None, None)
+                         None, None, None, self.debug)
         self.launches += 1
         return stats
 
