@@ -29,7 +29,7 @@ log = logging.getLogger("glint_word2vec_b200")
 JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
 _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "concurrency", "deterministic", "kernel",
-                "store_syn1", "window_mode", "sigmoid_mode", "max_grad", "device")
+                "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "device")
 
 
 def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:

@@ -43,4 +43,14 @@ int sgns_multi_max_grid(int K, int window, int negatives, int tile_centers, int 
 int sgns_single_grid(int K, int device);
 size_t sgns_multi_smem_bytes(int window, int negatives, int tile_centers);
 
+// sgns_pipe.cu: per-warp TMA pipeline variant of the single-shard step
+bool sgns_pipe_supported(int K, int window, int negatives);
+int sgns_pipe_grid(int K, int negatives, int device);
+void launch_sgns_pipe(const SgnsParams& p, int grid, cudaStream_t stream);
+
+// sgns_pipe_multi.cu: the pipeline with the in-kernel NVLink all-reduce (world > 1)
+bool sgns_pipe_multi_supported(int K, int window, int negatives);
+void sgns_pipe_multi_geometry(int K, int negatives, int device, int* grid, int* warps, int* nslot, int* slot_floats);
+void launch_sgns_pipe_multi(const SgnsParams& p, int grid, uint32_t* warp_seq, cudaStream_t stream);
+
 }  // namespace gw2v

@@ -44,7 +44,8 @@ class EngineOptions:
     batch_size: int = 50            # centres per mini-batch (reference ``batchSize``)
     step_tokens: int = 0            # tokens per device step (0 = auto)
     subsample_ratio: float = 1e-6
-    subsample_mode: str = "word2vec"    # "word2vec" | "reference" (Q1: inert)
+    subsample_mode: str = "reference"   # "reference" (Q1: the reference's sub-sampling is inert) | "word2vec"
+    max_hot_updates: int = 256          # auto step size: expected stale summed updates on the hottest row per step
     transport: str = "auto"         # auto | p2p | nvls | nccl | gloo
     concurrency: int = 0            # mini-batches in flight per step (0 = auto)
     deterministic: bool = False     # two-phase kernels (all dots, then all updates)
@@ -73,6 +74,7 @@ class ShardEngine:
         self.syn1: Optional[torch.Tensor] = None
         self.alias: Optional[AliasTable] = None
         self.keep_thresh: Optional[np.ndarray] = None
+        self.noise_counts: Optional[np.ndarray] = None
         self._norms: Optional[torch.Tensor] = None
         self._cuda = None
         if self.device.type == "cuda":
@@ -109,6 +111,7 @@ class ShardEngine:
         counts = np.asarray(counts, dtype=np.int64)
         if counts.shape[0] != self.cfg.vocab_size:
             raise ValueError("counts length != vocab size")
+        self.noise_counts = counts
         self.alias = unigram_alias(counts, 0.75, use_native=use_native)
         self.keep_thresh = keep_thresholds(counts, self.opts.subsample_ratio, self.opts.subsample_mode)
         if self.is_cuda:

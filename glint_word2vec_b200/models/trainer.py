@@ -47,16 +47,24 @@ class TrainReport:
 def auto_step_tokens(engine: ShardEngine, corpus_tokens: int) -> int:
     """Tokens per device step.
 
-    GPUs want enough mini-batches in flight to fill 148 SMs; tiny corpora want
-    few concurrent mini-batches so summed stale updates do not blow up (the
-    README's exploding-gradient warning, README.md:17-19).  Rule: at most 1/64
-    of an iteration per step, clamped to [batch_size, 256k]."""
+    On a GPU every centre of a step is in flight at once (thousands of warps), so
+    a row that occurs c times in the step receives c summed updates computed from
+    nearly the same stale values -- the asynchronous-SGD hazard the reference warns
+    about (README.md:17-19: "sensitive to very frequent words ... exploding
+    gradients").  The step is therefore sized so that the hottest word (after
+    sub-sampling) is expected at most ``max_hot_updates`` times per step, clamped to
+    [256, 256k] tokens; ``step_tokens`` overrides it."""
     opts = engine.opts
     if opts.step_tokens > 0:
         return opts.step_tokens
     if not engine.is_cuda:
         return max(opts.batch_size, min(1 << 16, corpus_tokens))
-    return int(max(opts.batch_size, min(1 << 18, max(corpus_tokens // 64, 1))))
+    f_max = 1.0
+    if engine.alias is not None and engine.keep_thresh is not None and engine.noise_counts is not None:
+        eff = engine.noise_counts.astype(np.float64) * (engine.keep_thresh.astype(np.float64) + 1.0) / 2.0 ** 32
+        f_max = float(eff.max() / max(eff.sum(), 1.0))
+    step = int(opts.max_hot_updates / max(f_max, 1e-9))
+    return int(max(256, min(1 << 18, step)))
 
 
 def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_iterations: int,

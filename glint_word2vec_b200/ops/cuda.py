@@ -97,26 +97,41 @@ class CudaShardOps:
 
     # ------------------------------------------------------------------ cross-shard exchange
     def _setup_exchange(self):
-        """Symmetric exchange slots + flags for the in-kernel all-reduce."""
+        """Symmetric exchange slots + flags for the in-kernel all-reduce (collective)."""
         from ..parallel.symm import alloc_symmetric
         cfg = self.cfg
-        tb = int(os.environ.get("GW2V_TILE_CENTERS", "16"))
-        grid = int(_C.sgns_multi_max_grid(self.K, cfg.window, cfg.negatives, tb, self.dev.index or 0))
-        # all ranks must launch the identical grid (the flag protocol pairs CTA c with CTA c)
-        g = torch.tensor([grid], dtype=torch.int64, device=self.dev)
+        dev_index = self.dev.index or 0
+        want = os.environ.get("GW2V_MULTI_KERNEL", "auto")
+        pipe_ok = bool(_C.sgns_pipe_multi_supported(self.K, cfg.window, cfg.negatives))
+        variant = 1 if (pipe_ok and want in ("auto", "pipe")) else 0
+        if variant == 1:
+            grid, warps, nslot, slot_floats = [int(x) for x in
+                                               _C.sgns_pipe_multi_geometry(self.K, cfg.negatives, dev_index)]
+            tb = 0
+            units = grid * warps                      # one exchange ring per warp
+            xbytes = units * nslot * self.world * slot_floats * 4
+            nseq = units
+        else:
+            tb = int(os.environ.get("GW2V_TILE_CENTERS", "16"))
+            grid = int(_C.sgns_multi_max_grid(self.K, cfg.window, cfg.negatives, tb, dev_index))
+            maxpairs = tb * 2 * cfg.window
+            slot_floats = (maxpairs * (1 + cfg.negatives) + 3) // 4 * 4
+            units = grid                              # one exchange ring (2 slots) per CTA
+            xbytes = units * 2 * self.world * slot_floats * 4
+            nseq = grid
+        # all ranks must launch the identical geometry (the flag protocol pairs warp w with warp w)
+        g = torch.tensor([grid, -grid], dtype=torch.int64, device=self.dev)
         dist.all_reduce(g, op=dist.ReduceOp.MIN, group=self.e.comm.group)
-        grid = int(g.item())
-        maxpairs = tb * 2 * cfg.window
-        slot_floats = (maxpairs * (1 + cfg.negatives) + 3) // 4 * 4
-        xbytes = grid * 2 * self.world * slot_floats * 4
-        fbytes = grid * self.world * 4
-        fbytes = (fbytes + 255) // 256 * 256
+        if int(g[0].item()) != grid or int(-g[1].item()) != grid:
+            raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
+        fbytes = (units * self.world * 4 + 255) // 256 * 256
+        xbytes = (xbytes + 255) // 256 * 256
         buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
         self._xchg = {
-            "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats,
+            "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats, "variant": variant,
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
             "mc": buf.multicast_ptr,
-            "cta_seq": torch.zeros(grid, dtype=torch.int32, device=self.dev),
+            "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
             "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
         }
         self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
@@ -174,14 +189,20 @@ class CudaShardOps:
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank, x["tb"],
                          x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing,
-                         self.debug)
+                         self.debug, x["variant"])
         else:
             if not hasattr(self, "_grid1"):
-                self._grid1 = int(_C.sgns_single_grid(self.K, self.dev.index or 0))
+                want = os.environ.get("GW2V_SINGLE_KERNEL", self.e.opts.kernel)
+                pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
+                self._variant = 1 if (pipe_ok and want in ("auto", "pipe", "fused")) else 0
+                if want == "v1":
+                    self._variant = 0
+                self._grid1 = int(_C.sgns_pipe_grid(self.K, cfg.negatives, self.dev.index or 0)) if self._variant == 1 \
+                    else int(_C.sgns_single_grid(self.K, self.dev.index or 0))
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
-                         None, None, None, self.debug)
+                         None, None, None, self.debug, self._variant)
         self.launches += 1
         return stats
 

@@ -27,18 +27,4 @@ def corpus_sentences():
     return synthetic_capitals_corpus()
 
 
-def synthetic_capitals_corpus(n_sent=6000, seed=0):
-    import random
-    rng = random.Random(seed)
-    pairs = [("österreich", "wien"), ("deutschland", "berlin"), ("frankreich", "paris"),
-             ("spanien", "madrid"), ("finnland", "helsinki"), ("grossbritannien", "london")]
-    filler = [f"w{i}" for i in range(300)]
-    sents = []
-    for _ in range(n_sent):
-        c, k = rng.choice(pairs)
-        s = [rng.choice(filler) for _ in range(rng.randint(3, 12))]
-        s.insert(rng.randint(0, len(s)), c)
-        s.insert(rng.randint(0, len(s)), k)
-        s.insert(rng.randint(0, len(s)), "hauptstadt")
-        sents.append(s)
-    return sents
+from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus  # noqa: E402,F401

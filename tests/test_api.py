@@ -79,7 +79,7 @@ def test_estimator_persistence(tmp_path):
 
 @pytest.fixture(scope="module")
 def small_model():
-    from conftest import synthetic_capitals_corpus
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
     sents = synthetic_capitals_corpus(3000, seed=1)
     est = ServerSideGlintWord2Vec(vectorSize=24, seed=5, stepSize=0.05, maxIter=3, minCount=2,
                                   numParameterServers=1, inputCol="sentence", outputCol="vec",

@@ -89,14 +89,16 @@ def _make_engine(dev, v, d, window=5, n=5, window_mode="reference", seed=7):
     return eng, counts
 
 
+@pytest.mark.parametrize("variant", ["pipe", "v1"])
 @pytest.mark.parametrize("d,window,n,wmode", [(64, 5, 5, "reference"), (100, 5, 5, "reference"),
                                               (128, 3, 7, "word2vec_c"), (512, 5, 5, "reference"),
                                               (300, 5, 10, "word2vec_c"), (40, 5, 5, "reference")])
-def test_sgns_step_single_matches_oracle(d, window, n, wmode):
+def test_sgns_step_single_matches_oracle(d, window, n, wmode, variant, monkeypatch):
     """Distinct centre/context tokens and V >> negatives: concurrent warps almost never
     re-read a row another warp has just updated, so the Hogwild kernel must match the
     summed mini-batch oracle closely (sequential-vs-batch oracle runs differ by < 1e-2 here)."""
     dev = _dev()
+    monkeypatch.setenv("GW2V_SINGLE_KERNEL", variant)     # pipe = per-warp TMA pipeline, v1 = register staging
     v = 200000
     eng, counts = _make_engine(dev, v, d, window, n, wmode)
     g = torch.Generator().manual_seed(0)
@@ -192,7 +194,7 @@ def test_fit_on_gpu_golden(corpus_sentences):
     from glint_word2vec_b200 import ServerSideGlintWord2Vec
     est = ServerSideGlintWord2Vec(seed=1, stepSize=0.025, numPartitions=2, numParameterServers=1,
                                   inputCol="sentence", outputCol="model", unigramTableSize=1000000,
-                                  parameterServerConfig={"subsample_mode": "reference", "step_tokens": 2000})
+                                  parameterServerConfig={"subsample_mode": "reference", "max_hot_updates": 16})
     model = est.fit({"sentence": corpus_sentences})
     try:
         syn = model.findSynonymsArray("österreich", 10)
@@ -200,5 +202,29 @@ def test_fit_on_gpu_golden(corpus_sentences):
         words = [w for w, _ in syn]
         assert "wien" in words
         assert dict(syn)["wien"] > 0.9
+        v = model.transformWord("wien") - model.transformWord("österreich") + model.transformWord("deutschland")
+        an = dict(model.findSynonymsArray(v, 10))
+        assert "berlin" in an and an["berlin"] > 0.9
     finally:
         model.stop()
+
+
+@pytest.mark.parametrize("k,q", [(64, 1), (64, 16), (128, 17), (512, 64), (256, 200), (32, 256)])
+def test_scores_tc_tcgen05_matches_fp32(k, q):
+    """tcgen05 (kind::tf32, TMEM accumulators, TMA operands) score GEMM vs an fp32 matmul."""
+    dev = _dev()
+    C = _C()
+    assert C.scores_tc_supported(k, q)
+    v = 30011                                            # not a multiple of the 128-row tile
+    g = torch.Generator().manual_seed(k * 1000 + q)
+    syn0 = torch.randn(v, k, generator=g).to(dev)
+    qs = torch.randn(q, k, generator=g).to(dev)
+    out = C.scores_tc(syn0, qs)
+    torch.cuda.synchronize()
+    ref = (qs.double() @ syn0.double().t()).float()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err / scale < 2e-3, (err, scale)              # tf32 operands (10-bit mantissa), fp32 accumulate
+    # the exact CUDA-core path agrees to fp32 rounding
+    out2 = C.scores_rows(syn0, qs[:8].contiguous())
+    assert torch.allclose(out2, ref[:8], rtol=1e-4, atol=1e-4)
