@@ -180,8 +180,9 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
         handle = open_handle_for_fit(cfg, vocab.counts, self.getParameterServerHost(),
                                      self.getNumParameterServers(), opts)
         try:
+            train_opts = {k: pcfg[k] for k in ("checkpoint_dir", "checkpoint_every_steps", "resume") if k in pcfg}
             report = handle.fit(corpus, self.getStepSize(), self.getMaxIter(), vocab.train_words,
-                                pcfg.get("metrics_path"))
+                                pcfg.get("metrics_path"), train_opts)
         except Exception:
             handle.destroy()
             handle.terminate(False)

@@ -16,7 +16,7 @@
 // Each warp owns S stages x (n+2) rows (context, n negatives, centre row for the first pair of a
 // centre; the same slot carries du for the last pair), so loads of later pairs are in flight while
 // the current one computes.  Warps are independent: no __syncthreads in the steady state.
-#include "common.cuh"
+#include "pipe_common.cuh"
 #include "sgns_params.h"
 
 namespace gw2v {
@@ -24,7 +24,7 @@ namespace gw2v {
 constexpr int V2_RING = 32;          // pair descriptors per warp
 constexpr int V2_ENTRY = 20;         // ints per descriptor: wtok, ctok, flags, pad, negs[<=16]
 constexpr int V2_MAXNEG = 16;
-constexpr int V2_RB = 6;
+constexpr int V2_RB = 8;
 
 __device__ __forceinline__ uint32_t smem_a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -234,22 +234,29 @@ sgns_fused_pipe_kernel(const SgnsParams p, const int nstage, const int stage_flo
 #pragma unroll
                 for (int r = 0; r < V2_RB; ++r) {
                     float sacc = 0.f;
+                    if (ract[r]) {
 #pragma unroll
-                    for (int c = 0; c < CHUNKS; ++c)
+                        for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
-                        for (int el = 0; el < VEC; ++el) sacc = fmaf(u[c][el], v[r][c][el], sacc);
-                    f[r] = warp_sum(sacc);
+                            for (int el = 0; el < VEC; ++el) sacc = fmaf(u[c][el], v[r][c][el], sacc);
+                    }
+                    f[r] = sacc;
+                }
+                // 8 dots reduced together; the lane owning row r computes its coefficient (and loss) once
+                const float ftot = reduce8_transposed(f, lane);
+                const int myrow = rb + row_of_lane(lane);
+                const float mylabel = (myrow == 0) ? 1.f : 0.f;
+                const float gmine = sgns_coeff(ftot, mylabel, p.alpha, p.max_grad);
+                const bool myact = (myrow <= n) && (myrow == 0 || e[4 + myrow - 1] != ctok);
+                if (p.compute_loss && myact && lane == lane_of_row(row_of_lane(lane))) {
+                    loss += softplus_clipped(mylabel > 0.5f ? -ftot : ftot);
+                    maxdot = fmaxf(maxdot, fabsf(ftot));
                 }
 #pragma unroll
                 for (int r = 0; r < V2_RB; ++r) {
+                    const float g = __shfl_sync(0xffffffffu, gmine, lane_of_row(r));
                     if (!ract[r]) continue;
                     const int k = rb + r;
-                    const float label = (k == 0) ? 1.f : 0.f;
-                    const float g = sgns_coeff(f[r], label, p.alpha, p.max_grad);
-                    if (p.compute_loss) {
-                        loss += softplus_clipped(label > 0.5f ? -f[r] : f[r]);
-                        maxdot = fmaxf(maxdot, fabsf(f[r]));
-                    }
 #pragma unroll
                     for (int c = 0; c < CHUNKS; ++c) {
                         if (!act[c]) continue;
@@ -284,6 +291,8 @@ sgns_fused_pipe_kernel(const SgnsParams p, const int nstage, const int stage_flo
     v2_wait_all();                       // smem must outlive the outstanding TMA reduces
 
     if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[3] = (float)T;
+    loss = warp_sum(loss);                 // per-lane partial sums (one owner lane per row)
+    maxdot = warp_max(maxdot);
     if (lane == 0 && pairs) {
         atomicAdd(p.stats + 0, (float)pairs);
         if (p.compute_loss) {

@@ -18,19 +18,18 @@
 // The schedule (when to push, when to update) is a pure function of per-warp counters, never of
 // timing, so the S ranks' warps stay in lock-step on batch boundaries without any negotiation.
 // Sequence numbers persist in device memory across launches and are never reset.
-#include "common.cuh"
+#include "pipe_common.cuh"
 #include "sgns_params.h"
 #include <cstdio>
 
 namespace gw2v {
 
-constexpr int M_RING = 32;           // pair descriptors per warp
-constexpr int M_ENTRY = 20;          // ints per descriptor
+constexpr int M_RING = 64;           // pair descriptors per warp (must exceed lag + stages + 2*window)
+constexpr int M_ENTRY = 12;          // ints per descriptor: wtok, ctok, flags, pad, negs[<=7]
 constexpr int M_MAXNEG = 7;          // 1 + n <= 8 floats per pair in an exchange slot
 constexpr int M_FP = 8;              // floats per pair in exchange slots
 constexpr int M_G = 4;               // pairs per batch (slot = 32 floats = 128 B)
 constexpr int M_RB = 8;
-constexpr int M_BQ = 64;             // batch bookkeeping ring (per warp)
 
 __device__ __forceinline__ uint32_t m_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void m_bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -79,20 +78,26 @@ __device__ __forceinline__ void m_sts(float* p, const float (&v)[VEC]) {
 }
 
 struct MultiPipeArgs {
-    int nstage;          // stages per warp
-    int prefetch;        // pairs of load look-ahead before dots
+    int nstage;          // smem stages per warp
+    int lag;             // pairs between the dots pass (A) and the update pass (B) of the same pair
     int stage_floats;    // (n + 2) * K
     int warp_bytes;      // smem per warp
-    int nslot;           // exchange slots per (cta, warp, source)
+    int nslot;           // exchange slots per (warp, source)
     uint32_t* warp_seq;  // [grid * warps] running batch sequence per warp (device memory, never reset)
 };
 
-// per-warp shared memory:  stages | mbarriers (128 B) | fpart[nstage][8] | ftot[nstage][8] | xsum[8][32]
-//                          | batch_end[M_BQ] | ring[M_RING][M_ENTRY]
-__host__ __device__ inline size_t m_fixed_bytes(int nstage) {
-    return 128 + (size_t)nstage * M_FP * 4 * 2 + 8 * 32 * 4 + M_BQ * 4 + (size_t)M_RING * M_ENTRY * 4;
+// per-warp shared memory:  stages | mbarriers (128 B) | fpart/ftot[M_RING][8] | xsum[8][32]
+//                          | item queue (M_IQ bytes) | ring[M_RING][M_ENTRY]
+constexpr int M_IQ = 64;
+__host__ __device__ inline size_t m_fixed_bytes() {
+    return 128 + (size_t)M_RING * M_FP * 4 + 8 * 32 * 4 + M_IQ + (size_t)M_RING * M_ENTRY * 4;
 }
 
+// Every pair passes through the stage ring twice:
+//   A item: TMA-load its rows, partial dots, (every M_G pairs) push the batch to all peers
+//   B item: `lag` pairs later TMA-load the rows again (L2 hits), reduce the S partials, update
+// The A/B interleaving is decided at issue time from per-warp counters only, recorded in a small
+// item queue and replayed at compute time, so all ranks follow the identical schedule.
 template <int VEC, int CHUNKS>
 __global__ void __launch_bounds__((CHUNKS >= 3) ? 256 : 512)
 sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
@@ -105,21 +110,21 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
     float* stages = reinterpret_cast<float*>(wbase);
     unsigned char* q = wbase + (size_t)nstage * a.stage_floats * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(q);            q += 128;
-    float* fpart = reinterpret_cast<float*>(q);                 q += (size_t)nstage * M_FP * 4;
-    float* ftot = reinterpret_cast<float*>(q);                  q += (size_t)nstage * M_FP * 4;
+    float* fpart = reinterpret_cast<float*>(q);                 q += (size_t)M_RING * M_FP * 4;
+    float* ftot = fpart;                                        // the reduced dots replace the partials in place
     float* xsum = reinterpret_cast<float*>(q);                  q += 8 * 32 * 4;
-    int* batch_end = reinterpret_cast<int*>(q);                 q += M_BQ * 4;
+    unsigned char* iq = q;                                      q += M_IQ;
     int* ring = reinterpret_cast<int*>(q);
 
     const int K = p.K;
     const int n = p.negatives;
-    const int np1 = n + 1;
     const int ncalls = (n + 1) >> 1;
     const uint32_t row_bytes = (uint32_t)K * 4u;
     const int T = *p.n_tokens;
     const int maxctx = 2 * p.window;
     const int S = p.world;
     const int rank = p.rank;
+    const int L = a.lag;
     const uint32_t sw_neg = stream_word(STREAM_NEG, p.iteration);
     const int gwarp = blockIdx.x * nwarp_cta + warp;            // identical on every rank
     const int n_warps = gridDim.x * nwarp_cta;
@@ -135,7 +140,6 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) { coff[c] = (c * 32 + lane) * VEC; act[c] = coff[c] < K; }
 
-    // exchange addressing: slot(seq) of (gwarp, src) on rank `peer`
     const size_t slot_stride = (size_t)M_G * M_FP;                               // floats per (slot, src)
     const size_t warp_x_base = (size_t)gwarp * a.nslot * S * slot_stride;
     uint32_t* my_flags = p.flags[rank] + (size_t)gwarp * S;
@@ -143,8 +147,13 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
     const uint32_t seq0 = seq;
 
     int gen_i = gwarp;
-    int head = 0, issued = 0, dots = 0, pushed = 0, upd = 0;    // pair counters (monotonic)
-    int nb_pushed = 0, nb_recv = 0;                             // batch counters (this launch)
+    int head = 0;                         // pairs generated
+    int ia = 0, ib = 0;                   // A / B items issued (pair indices)
+    int ca = 0, cb = 0;                   // A / B items computed
+    int items_issued = 0, items_done = 0; // positions in the item sequence
+    int pushed = 0;                       // pairs whose partials have been pushed
+    int nb_pushed = 0, nb_recv = 0, recv_end = 0;
+    bool last_was_b = false;              // previous occupant kind of each stage is tracked via iq as well
     float ud[CHUNKS][VEC], uu[CHUNKS][VEC], du[CHUNKS][VEC];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c)
@@ -153,10 +162,32 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
     float loss = 0.f, maxdot = 0.f;
     unsigned pairs = 0;
     unsigned long long wait_ns = 0;
+    (void)last_was_b;
+
+    // push pairs [pushed, ca) as one batch: lane j stores them into rank j's slot, then release-publishes seq+1
+    auto push_batch = [&]() {
+        __syncwarp();
+        const int slot = (int)(seq % (uint32_t)a.nslot);
+        if (lane < S && lane != rank) {
+            float4* dst = reinterpret_cast<float4*>(p.xbuf[lane] + warp_x_base +
+                                                    ((size_t)slot * S + rank) * slot_stride);
+            const int cnt = ca - pushed;
+            for (int g = 0; g < cnt; ++g) {
+                const float4* src = reinterpret_cast<const float4*>(fpart + ((pushed + g) % M_RING) * M_FP);
+                dst[g * 2 + 0] = src[0];
+                dst[g * 2 + 1] = src[1];
+            }
+            st_release_sys(p.flags[lane] + (size_t)gwarp * S + rank, seq + 1u);
+        }
+        __syncwarp();
+        pushed = ca;
+        ++nb_pushed;
+        ++seq;
+    };
 
     while (true) {
         // ---------------------------------------------------------------- (1) generate descriptors
-        while (gen_i < T && (M_RING - (head - upd)) >= maxctx) {
+        while (gen_i < T && (M_RING - (head - cb)) >= maxctx) {
             const int i = gen_i;
             gen_i += n_warps;
             uint4 rw = rand4(p.seed_lo, p.seed_hi, stream_word(STREAM_WINDOW, p.iteration),
@@ -203,18 +234,26 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
             head += npair;
         }
         __syncwarp();
+        const bool gen_done = gen_i >= T;
 
-        // ---------------------------------------------------------------- (2) issue TMA loads
-        while (issued < head && issued - upd < nstage) {
-            const int s = issued % nstage;
-            const int* e = ring + (issued % M_RING) * M_ENTRY;
+        // ---------------------------------------------------------------- (2) issue items (TMA loads)
+        while (items_issued - items_done < nstage) {
+            // deterministic choice of the next item: A while the dots pass is less than `lag` ahead, else B
+            int kind;                                     // 0 = A, 1 = B
+            if (ia < head && ia - ib < L) kind = 0;
+            else if (ib < ia && (ia - ib >= L || (gen_done && ia == head))) kind = 1;
+            else break;                                   // nothing issuable right now
+            const int pidx = kind ? ib : ia;
+            const int s = items_issued % nstage;
+            const int* e = ring + (pidx % M_RING) * M_ENTRY;
             float* stage = stages + (size_t)s * a.stage_floats;
-            if (issued >= nstage) m_wait_read0();
+            if (items_issued >= nstage && iq[(items_issued - nstage) % M_IQ]) m_wait_read0();   // previous occupant was a B item
             const int wtok = e[0], ctok = e[1], flags = e[2];
             if (lane == 0) {
                 int nact = 1 + (flags & 1);
                 for (int k = 0; k < n; ++k) nact += (e[4 + k] != ctok) ? 1 : 0;
                 m_mbar_expect_tx(bars + s, (uint32_t)nact * row_bytes);
+                iq[items_issued % M_IQ] = (unsigned char)kind;
             }
             __syncwarp();
             if (lane <= n) {
@@ -224,18 +263,27 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
             } else if (lane == n + 1 && (flags & 1)) {
                 m_bulk_load(stage + (size_t)(n + 1) * K, p.syn0 + (size_t)wtok * K, row_bytes, bars + s);
             }
-            ++issued;
+            if (kind) ++ib; else ++ia;
+            ++items_issued;
         }
 
-        const bool stream_done = (gen_i >= T) && (issued == head);
-        // ---------------------------------------------------------------- (3) dots (+ push)
-        // deterministic rule: run dots while the load look-ahead is satisfied (or nothing more can be issued)
-        if (dots < issued && ((issued - dots) > a.prefetch || stream_done)) {
-            const int s = dots % nstage;
-            const int* e = ring + (dots % M_RING) * M_ENTRY;
-            const float* stage = stages + (size_t)s * a.stage_floats;
+        // the stream ended after the last dots were computed: close the open batch (same decision on every rank)
+        if (gen_done && ia == head && ca == head && ca > pushed) push_batch();
+
+        if (items_done == items_issued) {
+            if (gen_done && cb == head) break;
+            continue;
+        }
+
+        // ---------------------------------------------------------------- (3) compute the next item
+        const int s = items_done % nstage;
+        const int kind = iq[items_done % M_IQ];
+        float* stage = stages + (size_t)s * a.stage_floats;
+        m_mbar_wait(bars + s, (uint32_t)((items_done / nstage) & 1));
+        if (kind == 0) {
+            // ---------------- A: partial dots of pair `ca`
+            const int* e = ring + (ca % M_RING) * M_ENTRY;
             const int ctok = e[1], flags = e[2];
-            m_mbar_wait(bars + s, (uint32_t)((dots / nstage) & 1));
             if (flags & 1) {
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
@@ -261,70 +309,64 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
                 }
                 f[r] = sacc;
             }
-#pragma unroll
-            for (int r = 0; r < M_RB; ++r) f[r] = warp_sum(f[r]);
-            if (lane < M_FP) {
-                float mine = 0.f;
-#pragma unroll
-                for (int r = 0; r < M_RB; ++r) if (lane == r) mine = f[r];
-                fpart[s * M_FP + lane] = mine;
+            {
+                const float tot = reduce8_transposed(f, lane);          // lane_of_row(r) holds the total of row r
+                const int myrow = row_of_lane(lane);
+                if (lane == lane_of_row(myrow)) fpart[(ca % M_RING) * M_FP + myrow] = tot;
             }
-            ++dots;
-            if (dots - pushed == M_G) goto do_push;
+            ++ca;
+            ++items_done;
+            // push when a batch is full, or when the stream ends with an open batch
+            if (ca - pushed == M_G || (gen_done && ca == head)) push_batch();
             continue;
         }
-        // ---------------------------------------------------------------- (4) update oldest pair
-        if (upd < dots) {
-            if (upd >= pushed) goto do_push;                 // its batch is still open: close it (deterministic)
-            // make sure the batch containing `upd` has been received and reduced
-            if (nb_recv < nb_pushed && upd >= (nb_recv == 0 ? 0 : batch_end[(nb_recv - 1) % M_BQ])) {
-                const int b_lo = (nb_recv == 0) ? 0 : batch_end[(nb_recv - 1) % M_BQ];
-                const int b_hi = batch_end[nb_recv % M_BQ];
-                const uint32_t bseq = seq0 + (uint32_t)nb_recv;
-                const int slot = (int)(bseq % (uint32_t)a.nslot);
-                float4 got[M_G * M_FP / 4];
-                if (lane < S && lane != rank) {
-                    unsigned long long t0 = p.timing ? globaltimer_ns() : 0ull;
-                    uint32_t spins = 0;
-                    while ((int32_t)(ld_acquire_sys(my_flags + lane) - (bseq + 1u)) < 0) {
-                        if ((++spins & 0xFFFu) == 0) {
-                            if (t0 == 0ull) t0 = globaltimer_ns();
-                            if (globaltimer_ns() - t0 > 20000000000ull) {
-                                printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u (flag %u)\n",
-                                       rank, gwarp, lane, bseq + 1u, ld_acquire_sys(my_flags + lane));
-                                atomicExch(p.error_flag, 1);
-                                __trap();
-                            }
+        // ---------------- B: reduce + update pair `cb`
+        if (cb >= recv_end) {
+            // receive the batch that starts at pair `cb`: pairs [cb, min(cb + M_G, pushed-at-that-time))
+            // batch boundaries are multiples of M_G except for the final partial batch
+            const int b_lo = cb;
+            const uint32_t bseq = seq0 + (uint32_t)nb_recv;
+            const int slot = (int)(bseq % (uint32_t)a.nslot);
+            if (lane < S && lane != rank) {
+                unsigned long long t0 = p.timing ? globaltimer_ns() : 0ull;
+                uint32_t spins = 0;
+                volatile uint32_t* fl = my_flags + lane;
+                while ((int32_t)(*fl - (bseq + 1u)) < 0) {
+                    if ((++spins & 0x3FFFu) == 0) {
+                        if (t0 == 0ull) t0 = globaltimer_ns();
+                        if (globaltimer_ns() - t0 > 20000000000ull) {
+                            printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u (flag %u)\n",
+                                   rank, gwarp, lane, bseq + 1u, *fl);
+                            atomicExch(p.error_flag, 1);
+                            __trap();
                         }
                     }
-                    if (p.timing) wait_ns += globaltimer_ns() - t0;
-                    const float4* src = reinterpret_cast<const float4*>(
-                        p.xbuf[rank] + warp_x_base + ((size_t)slot * S + lane) * slot_stride);
+                }
+                (void)ld_acquire_sys(my_flags + lane);          // acquire: the peer's data stores are visible
+                if (p.timing) wait_ns += globaltimer_ns() - t0;
+                const float4* src = reinterpret_cast<const float4*>(
+                    p.xbuf[rank] + warp_x_base + ((size_t)slot * S + lane) * slot_stride);
+                float4 got[M_G * M_FP / 4];
 #pragma unroll
-                    for (int v4 = 0; v4 < M_G * M_FP / 4; ++v4) got[v4] = __ldcg(src + v4);
+                for (int v4 = 0; v4 < M_G * M_FP / 4; ++v4) got[v4] = __ldcg(src + v4);
 #pragma unroll
-                    for (int v4 = 0; v4 < M_G * M_FP / 4; ++v4)
-                        reinterpret_cast<float4*>(xsum + lane * 32)[v4] = got[v4];
-                }
-                {   // own partials into the same layout: lane = pair_in_batch * 8 + value
-                    const int g = lane >> 3, vi = lane & 7;
-                    float mine = 0.f;
-                    if (b_lo + g < b_hi) mine = fpart[((b_lo + g) % nstage) * M_FP + vi];
-                    xsum[rank * 32 + lane] = mine;
-                }
-                __syncwarp();
-                {
-                    const int g = lane >> 3, vi = lane & 7;
-                    float tot = 0.f;
-                    for (int r = 0; r < S; ++r) tot += xsum[r * 32 + lane];      // fixed order: bit-identical on all ranks
-                    if (b_lo + g < b_hi) ftot[((b_lo + g) % nstage) * M_FP + vi] = tot;
-                }
-                __syncwarp();
-                ++nb_recv;
+                for (int v4 = 0; v4 < M_G * M_FP / 4; ++v4)
+                    reinterpret_cast<float4*>(xsum + lane * 32)[v4] = got[v4];
             }
-            const int s = upd % nstage;
-            const int* e = ring + (upd % M_RING) * M_ENTRY;
-            float* stage = stages + (size_t)s * a.stage_floats;
+            const int g = lane >> 3, vi = lane & 7;
+            // the batch holds min(M_G, pairs pushed beyond b_lo) pairs; a partial batch only occurs at the stream end
+            const int b_cnt = min(M_G, pushed - b_lo);
+            xsum[rank * 32 + lane] = (g < b_cnt) ? fpart[((b_lo + g) % M_RING) * M_FP + vi] : 0.f;
+            __syncwarp();
+            float tot = 0.f;
+            for (int r = 0; r < S; ++r) tot += xsum[r * 32 + lane];          // fixed order: bit-identical on all ranks
+            if (g < b_cnt) ftot[((b_lo + g) % M_RING) * M_FP + vi] = tot;
+            __syncwarp();
+            recv_end = b_lo + b_cnt;
+            ++nb_recv;
+        }
+        {
+            const int* e = ring + (cb % M_RING) * M_ENTRY;
             const int wtok = e[0], ctok = e[1], flags = e[2];
             if (flags & 1) {
 #pragma unroll
@@ -335,15 +377,23 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
                 }
             }
             ++pairs;
-            for (int r = 0; r <= n; ++r) {
-                if (r > 0 && e[4 + r - 1] == ctok) continue;
-                const float f = ftot[s * M_FP + r];
-                const float label = (r == 0) ? 1.f : 0.f;
-                const float g = sgns_coeff(f, label, p.alpha, p.max_grad);
-                if (p.compute_loss) {
+            const float* ft = ftot + (cb % M_RING) * M_FP;
+            // lane r (< 8) turns the reduced dot of row r into its coefficient / loss exactly once
+            float gmine = 0.f;
+            {
+                const int myrow = lane & 7;
+                const float f = ft[myrow];
+                const float label = (myrow == 0) ? 1.f : 0.f;
+                const bool myact = (myrow <= n) && (myrow == 0 || e[4 + myrow - 1] != ctok);
+                gmine = myact ? sgns_coeff(f, label, p.alpha, p.max_grad) : 0.f;
+                if (p.compute_loss && myact && lane < 8) {
                     loss += softplus_clipped(label > 0.5f ? -f : f);
                     maxdot = fmaxf(maxdot, fabsf(f));
                 }
+            }
+            for (int r = 0; r <= n; ++r) {
+                const float g = __shfl_sync(0xffffffffu, gmine, r);
+                if (r > 0 && e[4 + r - 1] == ctok) continue;
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
                     if (!act[c]) continue;
@@ -372,38 +422,17 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
                 m_bulk_reduce_add(p.syn0 + (size_t)wtok * K, stage + (size_t)(n + 1) * K, row_bytes);
             }
             m_commit();
-            ++upd;
-            continue;
-        }
-        if (stream_done && upd == head) break;
-        continue;
-
-    do_push:
-        {   // ---------------------------------------------------------- push pairs [pushed, dots) as one batch
-            __syncwarp();
-            const int slot = (int)(seq % (uint32_t)a.nslot);
-            if (lane < S && lane != rank) {
-                float4* dst = reinterpret_cast<float4*>(p.xbuf[lane] + warp_x_base +
-                                                        ((size_t)slot * S + rank) * slot_stride);
-                const int cnt = dots - pushed;
-                for (int g = 0; g < cnt; ++g) {
-                    const float4* src = reinterpret_cast<const float4*>(fpart + ((pushed + g) % nstage) * M_FP);
-                    dst[g * 2 + 0] = src[0];
-                    dst[g * 2 + 1] = src[1];
-                }
-                st_release_sys(p.flags[lane] + (size_t)gwarp * S + rank, seq + 1u);
-            }
-            if (lane == 0) batch_end[nb_pushed % M_BQ] = dots;
-            __syncwarp();
-            pushed = dots;
-            ++nb_pushed;
-            ++seq;
+            ++cb;
+            ++items_done;
         }
     }
     m_wait_all();
     if (lane == 0) a.warp_seq[gwarp] = seq;
+    (void)nb_pushed;
 
     if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[3] = (float)T;
+    loss = warp_sum(loss);
+    maxdot = warp_max(maxdot);
     if (lane == 0 && pairs) {
         atomicAdd(p.stats + 0, (float)pairs);
         if (p.compute_loss) {
@@ -420,7 +449,7 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
 
 // ------------------------------------------------------------------ host side
 
-struct MultiLayout { int warps, stages, prefetch, stage_floats, warp_bytes, nslot; size_t total; };
+struct MultiLayout { int warps, stages, lag, stage_floats, warp_bytes, nslot; size_t total; };
 
 static MultiLayout multi_layout(int K, int negatives) {
     MultiLayout best{0, 0, 0, 0, 0, 0, 0};
@@ -428,21 +457,20 @@ static MultiLayout multi_layout(int K, int negatives) {
     const int stage_floats = (negatives + 2) * K;
     const size_t stage_bytes = (size_t)stage_floats * 4;
     const int max_warps = (K > 256) ? 8 : 16;
+    const int lag = 16;                                  // pairs between dots and update = 4 batches in flight
     long best_score = -1;
     for (int warps = max_warps; warps >= 2; --warps) {
         size_t per_warp = (budget / warps) & ~(size_t)127;
-        // need at least 4 stages: >= 1 prefetch + >= 2 lag
         int stages = 0;
-        for (int st = 16; st >= 4; --st)
-            if (m_fixed_bytes(st) + (size_t)st * stage_bytes <= per_warp) { stages = st; break; }
+        for (int st = 8; st >= 3; --st)
+            if (m_fixed_bytes() + (size_t)st * stage_bytes <= per_warp) { stages = st; break; }
         if (stages == 0) continue;
-        // in-flight pairs per SM is what hides the NVLink round trip; more warps help issue
-        long score = (long)warps * stages * 4 + warps * (stages >= 8 ? 8 : stages);
+        long score = (long)warps * (stages > 4 ? 4 : stages) * 16 + warps;
         if (score > best_score) {
             best_score = score;
-            size_t wb = (m_fixed_bytes(stages) + (size_t)stages * stage_bytes + 127) & ~(size_t)127;
-            int prefetch = stages >= 12 ? 4 : (stages >= 8 ? 3 : (stages >= 6 ? 2 : 1));
-            best = MultiLayout{warps, stages, prefetch, stage_floats, (int)wb, 2 * (stages + 2) + 2, wb * warps};
+            size_t wb = (m_fixed_bytes() + (size_t)stages * stage_bytes + 127) & ~(size_t)127;
+            // batches in flight per warp <= lag / M_G + 2; slots must cover twice that (see the reuse argument)
+            best = MultiLayout{warps, stages, lag, stage_floats, (int)wb, 2 * (lag / M_G + 3), wb * warps};
         }
     }
     return best;
@@ -490,7 +518,7 @@ void sgns_pipe_multi_geometry(int K, int negatives, int device, int* grid, int* 
 
 void launch_sgns_pipe_multi(const SgnsParams& p, int grid, uint32_t* warp_seq, cudaStream_t stream) {
     MultiLayout l = multi_layout(p.K, p.negatives);
-    MultiPipeArgs a{l.stages, l.prefetch, l.stage_floats, l.warp_bytes, l.nslot, warp_seq};
+    MultiPipeArgs a{l.stages, l.lag, l.stage_floats, l.warp_bytes, l.nslot, warp_seq};
 #define CALL(V, C)                                                                                               \
     do {                                                                                                         \
         cudaFuncSetAttribute(sgns_fused_pipe_multi_kernel<V, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \

@@ -222,11 +222,18 @@ class CudaShardOps:
         self.launches += 1
         return _C.row_sqnorm(self.e.syn0)
 
-    def scores(self, qs: torch.Tensor) -> torch.Tensor:
-        """Partial scores [Q, V] of this shard's columns."""
+    def _use_tc(self, nq: int) -> bool:
+        """tcgen05 (tf32) screening pays off once the CUDA-core sweep turns compute bound (Q >= 8)."""
+        mode = os.environ.get("GW2V_NN_TC", "auto")
+        if mode == "0" or not _C.scores_tc_supported(self.K, nq):
+            return False
+        return mode == "1" or nq >= int(os.environ.get("GW2V_NN_TC_MIN_Q", "8"))
+
+    def scores(self, qs: torch.Tensor, allow_tc: bool = False) -> torch.Tensor:
+        """Partial scores [Q, V] of this shard's columns (exact fp32 unless ``allow_tc``)."""
         qs = qs.contiguous()
         self.launches += 1
-        if _C.scores_tc_supported(self.K, qs.shape[0]) and os.environ.get("GW2V_NN_TC", "1") == "1":
+        if allow_tc and self._use_tc(qs.shape[0]):
             return _C.scores_tc(self.e.syn0, qs)
         outs = []
         maxq = max(1, (192 * 1024) // (self.K * 4))
@@ -235,8 +242,24 @@ class CudaShardOps:
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def top_k(self, qs: torch.Tensor, norms: torch.Tensor, k: int):
-        part = self.scores(qs)
+        """Cosine top-k.  Large query batches are screened on the tensor cores (tf32) with a
+        margin, then the few surviving candidates are re-scored in exact fp32, so reported
+        similarities never carry tf32 rounding."""
+        nq = qs.shape[0]
+        v = self.cfg.vocab_size
+        tc = self._use_tc(nq)
+        part = self.scores(qs, allow_tc=tc)
         full = self.e.comm.all_reduce_sum(part)
-        self.launches += 2
-        idx, sim = _C.cosine_topk(full, norms.contiguous(), int(k))
-        return idx, sim
+        self.launches += 1
+        if not tc:
+            return _C.cosine_topk(full, norms.contiguous(), int(k))
+        kk = min(v, int(k) + 16)
+        idx, _ = _C.cosine_topk(full, norms.contiguous(), kk)            # [Q, kk] candidates
+        rows = _C.gather_rows(self.e.syn0, idx.reshape(-1).contiguous()).view(nq, kk, self.K)
+        self.launches += 1
+        dots = (rows * qs[:, None, :]).sum(-1)                           # exact fp32 partial dots (tiny)
+        dots = self.e.comm.all_reduce_sum(dots.contiguous())
+        nr = norms[idx]
+        cos = torch.where(nr > 0, dots / nr.clamp(min=1e-30), torch.zeros_like(dots))
+        sim, order = torch.sort(cos, dim=1, descending=True)
+        return torch.gather(idx, 1, order)[:, :k].contiguous(), sim[:, :k].contiguous()

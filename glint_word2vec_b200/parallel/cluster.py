@@ -45,13 +45,37 @@ from . import server as _server
 from .comm import Comm, comm_from_env
 
 
+def run_training(engine, corpus, lr, iters, train_words, metrics_path=None, train_opts=None):
+    """Plain run, checkpointed run, or resume-from-checkpoint (models/checkpoint.py)."""
+    from ..models import checkpoint
+    o = dict(train_opts or {})
+    ckdir, every = o.get("checkpoint_dir"), int(o.get("checkpoint_every_steps", 0) or 0)
+    if ckdir and o.get("resume") and checkpoint.latest(ckdir):
+        import json
+        with open(os.path.join(checkpoint.latest(ckdir), "state.json")) as f:
+            st = json.load(f)
+        engine.opts.step_tokens = int(st["step_tokens"])
+        from ..models import matrix_io as _mio
+        loaded = _mio.load_matrix(checkpoint.latest(ckdir), engine.comm, engine.device, engine.opts)
+        engine.syn0, engine.syn1 = loaded.syn0, loaded.syn1
+        ck = checkpoint.Checkpointer(engine, ckdir, every, {k: st[k] for k in (
+            "learning_rate", "num_iterations", "train_words", "step_tokens")}) if every > 0 else None
+        return trainer.train(engine, corpus, st["learning_rate"], st["num_iterations"], st["train_words"],
+                             metrics_path=metrics_path, checkpoint_fn=ck, start_iteration=st["iteration"],
+                             start_step=st["next_step"])
+    if ckdir and every > 0:
+        return checkpoint.train_with_checkpoints(engine, corpus, lr, iters, train_words, ckdir, every, metrics_path)
+    return trainer.train(engine, corpus, lr, iters, train_words, metrics_path=metrics_path)
+
+
 class MatrixHandle:
     """Interface shared by all handles (the reference's call-site contract)."""
     num_shards: int = 1
     cols: int = 0                      # == vectorSize (``matrix.cols`` MLLIB:473)
     host: str = ""                     # what to persist as ``parameterServerHost``
 
-    def fit(self, corpus: EncodedCorpus, lr: float, iters: int, train_words: int, metrics_path=None) -> dict:
+    def fit(self, corpus: EncodedCorpus, lr: float, iters: int, train_words: int, metrics_path=None,
+            train_opts=None) -> dict:
         raise NotImplementedError
 
     def pull(self, rows) -> np.ndarray: raise NotImplementedError
@@ -86,8 +110,8 @@ class InProcessHandle(MatrixHandle):
         eng = matrix_io.load_matrix(path, comm or comm_from_env(), device, EngineOptions.from_dict(opts))
         return cls(eng)
 
-    def fit(self, corpus, lr, iters, train_words, metrics_path=None):
-        rep = trainer.train(self.engine, corpus, lr, iters, train_words, metrics_path=metrics_path)
+    def fit(self, corpus, lr, iters, train_words, metrics_path=None, train_opts=None):
+        rep = run_training(self.engine, corpus, lr, iters, train_words, metrics_path, train_opts)
         self.last_report = {k: getattr(rep, k) for k in
                             ("iterations", "steps", "words", "pairs", "loss_per_pair", "max_abs_dot",
                              "seconds", "final_alpha")}
@@ -177,9 +201,9 @@ class RemoteHandle(MatrixHandle):
         self.cols = r["cols"]
         return r
 
-    def fit(self, corpus, lr, iters, train_words, metrics_path=None):
+    def fit(self, corpus, lr, iters, train_words, metrics_path=None, train_opts=None):
         self.last_report = self._call("fit", self.matrix_id, corpus.tokens, corpus.offsets, lr, iters,
-                                      train_words, metrics_path, timeout=7 * 24 * 3600.0)
+                                      train_words, metrics_path, train_opts, timeout=7 * 24 * 3600.0)
         return self.last_report
 
     def pull(self, rows):

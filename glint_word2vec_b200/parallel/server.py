@@ -95,10 +95,11 @@ class ShardServer:
         self.engines[mid] = eng
         return {"cols": eng.cfg.vector_size, "shards": self.comm.world}
 
-    def op_fit(self, mid, tokens, offsets, lr, iters, train_words, metrics_path=None):
+    def op_fit(self, mid, tokens, offsets, lr, iters, train_words, metrics_path=None, train_opts=None):
+        from .cluster import run_training
         eng = self._eng(mid)
         corpus = EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64))
-        rep = trainer.train(eng, corpus, lr, iters, train_words, metrics_path=metrics_path)
+        rep = run_training(eng, corpus, lr, iters, train_words, metrics_path, train_opts)
         out = {k: getattr(rep, k) for k in ("iterations", "steps", "words", "pairs", "loss_per_pair",
                                              "max_abs_dot", "seconds", "final_alpha")}
         out["history"] = rep.history[-50:]
@@ -245,7 +246,9 @@ def rank_main(rank: int, world: int, port: int, master_port: int, device_type: s
         torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
     comm: Comm
     if world > 1:
-        init_process_group(rank=rank, world=world, master_port=master_port, device=device)
+        # ranks idle inside a collective while rank 0 waits for client requests: no short time-out here
+        init_process_group(rank=rank, world=world, master_port=master_port, device=device,
+                           timeout_s=30 * 24 * 3600.0)
         comm = TorchDistComm()
     else:
         comm = Comm()

@@ -174,3 +174,42 @@ def test_zero_iterations_leaves_random_init():
     before = eng.syn0.clone()
     rep = trainer.train(eng, EncodedCorpus(np.arange(50, dtype=np.int32), np.array([0, 50])), 0.025, 0)   # Q8
     assert rep.pairs == 0 and torch.equal(eng.syn0, before)
+
+
+def test_checkpoint_resume_reproduces_uninterrupted_run(tmp_path):
+    """Kill-and-resume == uninterrupted run (bitwise on CPU), also across a shard-count change."""
+    from glint_word2vec_b200.models import checkpoint
+    v, d = 1500, 32
+    counts = zipf_counts(v, 10 ** 5)
+    toks = zipf_tokens(build_alias(counts.astype(np.float64)), 12000, seed=8)
+    corpus = EncodedCorpus(toks, np.arange(0, 12001, 40, dtype=np.int64))
+
+    def fresh():
+        e = ShardEngine(SGNSConfig(v, d, seed=4), device=torch.device("cpu"),
+                        options=EngineOptions(batch_size=100, step_tokens=1000))
+        e.init_weights()
+        e.set_noise(counts)
+        return e
+    ref = fresh()
+    trainer.train(ref, corpus, 0.05, 2, train_words=12000)
+    # interrupted run: checkpoint every 5 steps, "crash" after 17 steps
+    run = fresh()
+    ck = checkpoint.Checkpointer(run, str(tmp_path), 5, dict(learning_rate=0.05, num_iterations=2,
+                                                             train_words=12000, step_tokens=1000))
+    class Crash(Exception):
+        pass
+    n = {"steps": 0}
+
+    def fn(k, s):
+        ck(k, s)
+        n["steps"] += 1
+        if n["steps"] == 17:
+            raise Crash()
+    with pytest.raises(Crash):
+        trainer.train(run, corpus, 0.05, 2, train_words=12000, checkpoint_fn=fn)
+    path = checkpoint.latest(str(tmp_path))
+    assert path is not None and path.endswith("ckpt-0001-00000003")      # 12 steps/iteration -> step 15 = (1, 3)
+    eng, rep = checkpoint.resume(str(tmp_path), corpus, counts, Comm(), torch.device("cpu"),
+                                 EngineOptions(batch_size=100))
+    assert torch.equal(eng.syn0, ref.syn0) and torch.equal(eng.syn1, ref.syn1)
+    assert rep.steps == 24 - 15

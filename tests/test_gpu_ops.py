@@ -186,6 +186,15 @@ def test_inference_kernels_match_torch():
     rs, ri = torch.topk(cos, 12, dim=1)
     assert torch.allclose(sim, rs, rtol=1e-4, atol=1e-5)
     assert (idx == ri).float().mean() > 0.95              # ties may permute
+    # a large query batch goes through the tcgen05 (tf32) screen + exact fp32 re-rank
+    q16 = torch.randn(16, d)
+    idx16, sim16 = eng.top_k(q16, 10)
+    qn16 = q16 / q16.norm(dim=1, keepdim=True)
+    cos16 = (qn16 @ full.t()) / torch.where(nr > 0, nr, torch.ones_like(nr))
+    cos16[:, nr == 0] = 0
+    rs16, ri16 = torch.topk(cos16, 10, dim=1)
+    assert torch.allclose(sim16, rs16, rtol=1e-4, atol=1e-5)
+    assert (idx16 == ri16).float().mean() > 0.95
 
 
 def test_fit_on_gpu_golden(corpus_sentences):
