@@ -62,7 +62,7 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
         TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
         TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
         TORCH_CHECK(cta_seq.has_value() && error_flag.has_value(), "cta_seq/error_flag required");
-        TORCH_CHECK(variant == 1 || (tile_centers >= 1 && tile_centers <= 256), "tile_centers must be in [1, 256]");
+        TORCH_CHECK(variant >= 1 || (tile_centers >= 1 && tile_centers <= 256), "tile_centers must be in [1, 256]");
         for (int r = 0; r < world; ++r) {
             p.xbuf[r] = reinterpret_cast<float*>(xbuf_ptrs[r]);
             p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
@@ -71,12 +71,18 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
         p.cta_seq = reinterpret_cast<uint32_t*>(cta_seq->data_ptr<int>());
         p.error_flag = error_flag->data_ptr<int>();
         p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
-        if (variant == 1) {
+        if (variant == 2) {
+            TORCH_CHECK(gw2v::sgns_group_multi_supported(p.K, p.window, p.negatives), "group-multi kernel: unsupported shape");
+            gw2v::launch_sgns_group_multi(p, (int)grid, p.cta_seq, cur_stream());
+        } else if (variant == 1) {
             TORCH_CHECK(gw2v::sgns_pipe_multi_supported(p.K, p.window, p.negatives), "pipe-multi kernel: unsupported shape");
             gw2v::launch_sgns_pipe_multi(p, (int)grid, p.cta_seq, cur_stream());
         } else {
             gw2v::launch_sgns_multi(p, (int)grid, cur_stream());
         }
+    } else if (variant == 2) {
+        TORCH_CHECK(gw2v::sgns_group_supported(p.K, p.window, p.negatives), "group kernel does not support this shape");
+        gw2v::launch_sgns_group(p, (int)grid, cur_stream());
     } else if (variant == 1) {
         TORCH_CHECK(gw2v::sgns_pipe_supported(p.K, p.window, p.negatives), "pipe kernel does not support this shape");
         gw2v::launch_sgns_pipe(p, (int)grid, cur_stream());
@@ -223,6 +229,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgns_pipe_grid", [](int64_t K, int64_t n, int64_t dev) {
         c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
         return (int64_t)gw2v::sgns_pipe_grid((int)K, (int)n, (int)dev); });
+    m.def("sgns_group_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_group_supported((int)K, (int)w, (int)n); });
+    m.def("sgns_group_grid", [](int64_t K, int64_t dev) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
+        return (int64_t)gw2v::sgns_group_grid((int)K, (int)dev); });
+    m.def("sgns_group_multi_supported", [](int64_t K, int64_t w, int64_t n) {
+        return gw2v::sgns_group_multi_supported((int)K, (int)w, (int)n); });
+    m.def("sgns_group_multi_geometry", [](int64_t K, int64_t dev) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
+        int grid, warps, nslot, sf;
+        gw2v::sgns_group_multi_geometry((int)K, (int)dev, &grid, &warps, &nslot, &sf);
+        return std::vector<int64_t>{grid, warps, nslot, sf}; });
     m.def("sgns_pipe_multi_supported", [](int64_t K, int64_t w, int64_t n) {
         return gw2v::sgns_pipe_multi_supported((int)K, (int)w, (int)n); });
     m.def("sgns_pipe_multi_geometry", [](int64_t K, int64_t n, int64_t dev) {

@@ -98,13 +98,14 @@ __device__ __forceinline__ float group_reduce8(const float (&f)[8], int lane) {
 // then all 32 lanes share the Philox + alias-table work of the negatives.  Appends descriptors to
 // the warp's ring; returns the number of pairs appended.  Decisions are bit-identical to the CPU
 // oracle (models/sgns.py) and to the v1 kernels.
+template <int GEN = PIPE_GEN, int RING = PIPE_RING>
 __device__ __forceinline__ int generate_pairs(const SgnsParams& p, int T, int& gen_i, int n_warps, int* ring,
                                               int head, int lane) {
     const int n = p.negatives;
     const int ncalls = (n + 1) >> 1;
     int i = -1, lo = 0, hi = -1, wtok = 0;
     unsigned cmask = 0;                                  // valid context offsets of this lane's centre
-    if (lane < PIPE_GEN) {
+    if (lane < GEN) {
         const long long ci = (long long)gen_i + (long long)lane * n_warps;
         if (ci < T) {
             i = (int)ci;
@@ -123,15 +124,15 @@ __device__ __forceinline__ int generate_pairs(const SgnsParams& p, int T, int& g
         }
     }
     {   // advance the warp's centre cursor past this round (clamped; uniform)
-        const long long nx = (long long)gen_i + (long long)PIPE_GEN * n_warps;
+        const long long nx = (long long)gen_i + (long long)GEN * n_warps;
         gen_i = nx > (long long)T ? T : (int)nx;
     }
     const int cnt = __popc(cmask);
-    // exclusive prefix over the PIPE_GEN lanes
+    // exclusive prefix over the GEN lanes
     int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < PIPE_GEN; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    const int total = __shfl_sync(0xffffffffu, incl, PIPE_GEN - 1);
+    for (int o = 1; o < GEN; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, GEN - 1);
     if (total == 0) return 0;
     int base = head + incl - cnt;
     // descriptors: centre lanes write {wtok, ctok, i, slot}
@@ -140,7 +141,7 @@ __device__ __forceinline__ int generate_pairs(const SgnsParams& p, int T, int& g
         while (m) {
             const int q = __ffs(m) - 1;
             m &= m - 1;
-            int* e = ring + (base % PIPE_RING) * PIPE_ENTRY;
+            int* e = ring + (base % RING) * PIPE_ENTRY;
             e[0] = wtok;
             e[1] = __ldg(p.tokens + i + lo + q);
             e[2] = i;
@@ -153,7 +154,7 @@ __device__ __forceinline__ int generate_pairs(const SgnsParams& p, int T, int& g
     const uint32_t sw_neg = stream_word(STREAM_NEG, p.iteration);
     for (int item = lane; item < total * ncalls; item += 32) {
         const int pr = item / ncalls, c = item - pr * ncalls;
-        int* e = ring + ((head + pr) % PIPE_RING) * PIPE_ENTRY;
+        int* e = ring + ((head + pr) % RING) * PIPE_ENTRY;
         uint4 r = rand4(p.seed_lo, p.seed_hi, sw_neg, p.pos0 + (unsigned long long)e[2], (uint32_t)(e[3] * ncalls + c));
         e[4 + 2 * c] = alias_sample(p.alias, (uint32_t)p.vocab, r.x, r.y);
         if (2 * c + 1 < n) e[4 + 2 * c + 1] = alias_sample(p.alias, (uint32_t)p.vocab, r.z, r.w);

@@ -48,6 +48,16 @@ bool sgns_pipe_supported(int K, int window, int negatives);
 int sgns_pipe_grid(int K, int negatives, int device);
 void launch_sgns_pipe(const SgnsParams& p, int grid, cudaStream_t stream);
 
+// sgns_group.cu: register-path kernel with lane groups (short rows / high occupancy)
+bool sgns_group_supported(int K, int window, int negatives);
+int sgns_group_grid(int K, int device);
+void launch_sgns_group(const SgnsParams& p, int grid, cudaStream_t stream);
+
+// sgns_group_multi.cu: lane-group register path with the in-kernel NVLink all-reduce (world > 1)
+bool sgns_group_multi_supported(int K, int window, int negatives);
+void sgns_group_multi_geometry(int K, int device, int* grid, int* warps, int* nslot, int* slot_floats);
+void launch_sgns_group_multi(const SgnsParams& p, int grid, uint32_t* warp_seq, cudaStream_t stream);
+
 // sgns_pipe_multi.cu: the pipeline with the in-kernel NVLink all-reduce (world > 1)
 bool sgns_pipe_multi_supported(int K, int window, int negatives);
 void sgns_pipe_multi_geometry(int K, int negatives, int device, int* grid, int* warps, int* nslot, int* slot_floats);

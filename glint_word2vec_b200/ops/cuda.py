@@ -103,10 +103,14 @@ class CudaShardOps:
         dev_index = self.dev.index or 0
         want = os.environ.get("GW2V_MULTI_KERNEL", "auto")
         pipe_ok = bool(_C.sgns_pipe_multi_supported(self.K, cfg.window, cfg.negatives))
-        variant = 1 if (pipe_ok and want in ("auto", "pipe")) else 0
-        if variant == 1:
-            grid, warps, nslot, slot_floats = [int(x) for x in
-                                               _C.sgns_pipe_multi_geometry(self.K, cfg.negatives, dev_index)]
+        group_ok = bool(_C.sgns_group_multi_supported(self.K, cfg.window, cfg.negatives))
+        if want == "auto":
+            want = "group" if group_ok else ("pipe" if pipe_ok else "v1")
+        variant = 2 if (want == "group" and group_ok) else (1 if (want == "pipe" and pipe_ok) else 0)
+        if variant >= 1:
+            geo = _C.sgns_group_multi_geometry(self.K, dev_index) if variant == 2 else \
+                _C.sgns_pipe_multi_geometry(self.K, cfg.negatives, dev_index)
+            grid, warps, nslot, slot_floats = [int(x) for x in geo]
             tb = 0
             units = grid * warps                      # one exchange ring per warp
             xbytes = units * nslot * self.world * slot_floats * 4
@@ -192,19 +196,30 @@ class CudaShardOps:
                          self.debug, x["variant"])
         else:
             if not hasattr(self, "_grid1"):
-                want = os.environ.get("GW2V_SINGLE_KERNEL", self.e.opts.kernel)
-                pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
-                self._variant = 1 if (pipe_ok and want in ("auto", "pipe", "fused")) else 0
-                if want == "v1":
-                    self._variant = 0
-                self._grid1 = int(_C.sgns_pipe_grid(self.K, cfg.negatives, self.dev.index or 0)) if self._variant == 1 \
-                    else int(_C.sgns_single_grid(self.K, self.dev.index or 0))
+                self._variant, self._grid1 = self._pick_single_kernel()
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
                          None, None, None, self.debug, self._variant)
         self.launches += 1
         return stats
+
+    def _pick_single_kernel(self):
+        """single-shard kernel variant: 2 = lane-group register path, 1 = TMA pipeline, 0 = v1."""
+        cfg = self.cfg
+        dev_index = self.dev.index or 0
+        want = os.environ.get("GW2V_SINGLE_KERNEL", "auto")
+        group_ok = bool(_C.sgns_group_supported(self.K, cfg.window, cfg.negatives))
+        pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
+        if want == "auto":
+            # measured on B200 (profiles/r1_kernel_variants.md): the lane-group register path wins at every
+            # row length (TMA bulk copies cost ~25 SM cycles each, which binds the pipeline for short rows)
+            want = "group" if group_ok else ("pipe" if pipe_ok else "v1")
+        if want == "group" and group_ok:
+            return 2, int(_C.sgns_group_grid(self.K, dev_index))
+        if want == "pipe" and pipe_ok:
+            return 1, int(_C.sgns_pipe_grid(self.K, cfg.negatives, dev_index))
+        return 0, int(_C.sgns_single_grid(self.K, dev_index))
 
     # ------------------------------------------------------------------ inference
     def _rows_dev(self, rows: torch.Tensor) -> torch.Tensor:
