@@ -92,6 +92,68 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
     check_launch("sgns_step");
 }
 
+// pair generation + the pair-parallel training kernel (single shard or column shards with in-kernel exchange)
+void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n_tokens, int64_t max_tokens,
+                     Tensor alias, Tensor stats, int64_t pos0, int64_t seed, int64_t iteration, int64_t window,
+                     int64_t negatives, int64_t window_mode, double alpha, double max_grad, bool compute_loss,
+                     int64_t grid, int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs,
+                     std::vector<int64_t> flag_ptrs, c10::optional<Tensor> warp_seq, c10::optional<Tensor> error_flag,
+                     c10::optional<Tensor> timing, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs,
+                     Tensor desc, Tensor ticket, Tensor chain, int64_t epoch) {
+    CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
+    CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
+    CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
+    CHECK_DT(alias, torch::kInt32); CHECK_DT(stats, torch::kFloat32); CHECK_DT(cinfo, torch::kInt32);
+    CHECK_DT(pair_off, torch::kInt32); CHECK_DT(n_pairs, torch::kInt32); CHECK_DT(desc, torch::kInt32);
+    CHECK_DT(ticket, torch::kInt32); CHECK_DT(chain, torch::kInt64);
+    TORCH_CHECK(gw2v::sgns_pairs_supported((int)syn0.size(1), (int)window, (int)negatives), "sgns_pairs: unsupported shape");
+    const int pd = gw2v::pairgen_desc_ints((int)negatives);
+    TORCH_CHECK(cinfo.numel() >= max_tokens && pair_off.numel() >= max_tokens, "pairgen workspaces too small");
+    TORCH_CHECK(desc.numel() >= max_tokens * 2 * window * pd, "descriptor buffer too small");
+    TORCH_CHECK(chain.numel() >= gw2v::pairgen_max_blocks((int)max_tokens), "chain buffer too small");
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::SgnsParams p{};
+    p.syn0 = syn0.data_ptr<float>();
+    p.syn1 = syn1.data_ptr<float>();
+    p.tokens = tokens.data_ptr<int>();
+    p.sent_id = sent_id.data_ptr<int>();
+    p.n_tokens = n_tokens.data_ptr<int>();
+    p.alias = reinterpret_cast<const int2*>(alias.data_ptr<int>());
+    p.stats = stats.data_ptr<float>();
+    p.pos0 = (unsigned long long)pos0;
+    p.seed_lo = (uint32_t)((uint64_t)seed & 0xFFFFFFFFull);
+    p.seed_hi = (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull);
+    p.iteration = (uint32_t)iteration;
+    p.vocab = (int)syn0.size(0);
+    p.K = (int)syn0.size(1);
+    p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
+    p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
+    p.debug = (int)debug;
+    p.world = (int)world; p.rank = (int)rank;
+    gw2v::launch_pairgen(p.tokens, p.sent_id, p.n_tokens, (int)max_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi,
+                         p.iteration, p.pos0, p.window, p.window_mode, p.negatives,
+                         reinterpret_cast<uint32_t*>(cinfo.data_ptr<int>()), pair_off.data_ptr<int>(),
+                         n_pairs.data_ptr<int>(), desc.data_ptr<int>(),
+                         reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()),
+                         reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch, cur_stream());
+    if (world > 1) {
+        TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
+        TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
+        TORCH_CHECK(warp_seq.has_value() && error_flag.has_value(), "warp_seq/error_flag required");
+        for (int r = 0; r < world; ++r) {
+            p.xbuf[r] = reinterpret_cast<float*>(xbuf_ptrs[r]);
+            p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+        }
+        p.error_flag = error_flag->data_ptr<int>();
+        p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
+        gw2v::launch_sgns_pairs_multi(p, desc.data_ptr<int>(), n_pairs.data_ptr<int>(), pd, (int)grid,
+                                      reinterpret_cast<uint32_t*>(warp_seq->data_ptr<int>()), cur_stream());
+    } else {
+        gw2v::launch_sgns_pairs(p, desc.data_ptr<int>(), n_pairs.data_ptr<int>(), pd, (int)grid, cur_stream());
+    }
+    check_launch("sgns_step_pairs");
+}
+
 int64_t sgns_single_grid(int64_t K, int64_t device) { return gw2v::sgns_single_grid((int)K, (int)device); }
 int64_t sgns_multi_max_grid(int64_t K, int64_t window, int64_t negatives, int64_t tile_centers, int64_t device) {
     c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
@@ -223,6 +285,15 @@ bool scores_tc_supported(int64_t K, int64_t Q) { return gw2v::scores_tc_supporte
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgns_step", &sgns_step);
+    m.def("sgns_step_pairs", &sgns_step_pairs);
+    m.def("sgns_pairs_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_pairs_supported((int)K, (int)w, (int)n); });
+    m.def("sgns_pairs_grid", [](int64_t K, int64_t dev, bool multi) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
+        return (int64_t)gw2v::sgns_pairs_grid((int)K, (int)dev, multi); });
+    m.def("sgns_pairs_multi_geometry", []() {
+        int w, ns, sf; gw2v::sgns_pairs_multi_geometry(&w, &ns, &sf); return std::vector<int64_t>{w, ns, sf}; });
+    m.def("pairgen_max_blocks", [](int64_t t) { return (int64_t)gw2v::pairgen_max_blocks((int)t); });
+    m.def("pairgen_desc_ints", [](int64_t n) { return (int64_t)gw2v::pairgen_desc_ints((int)n); });
     m.def("sgns_single_grid", &sgns_single_grid);
     m.def("sgns_multi_max_grid", &sgns_multi_max_grid);
     m.def("sgns_pipe_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_pipe_supported((int)K, (int)w, (int)n); });

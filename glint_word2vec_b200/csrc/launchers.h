@@ -17,6 +17,14 @@ void launch_zipf_stream(const int2* alias, int vocab, uint32_t seed_lo, uint32_t
 void launch_init_syn0(float* syn0, long long vocab, int K, int col_start, int vector_size, uint32_t seed_lo,
                       uint32_t seed_hi, cudaStream_t stream);
 
+// pairgen.cu
+int pairgen_max_blocks(int max_tokens);
+int pairgen_desc_ints(int negatives);
+void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
+                    int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
+                    int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
+                    int* desc, unsigned int* ticket, unsigned long long* chain, uint32_t epoch, cudaStream_t stream);
+
 // infer_kernels.cu
 void launch_gather_rows(const float* syn0, const long long* rows, int R, int K, float* out, cudaStream_t s);
 void launch_segment_mean_rows(const float* syn0, const long long* rows, const long long* offsets, int NS, int K,

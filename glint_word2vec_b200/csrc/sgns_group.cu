@@ -13,6 +13,7 @@
 //   * the 8 dots of a pair are reduced by one transposed butterfly, each sigmoid is evaluated once.
 // Semantics: per-pair private negatives; u is re-read and du applied per pair (word2vec.c order).
 #include "pipe_common.cuh"
+#include <cstdlib>
 
 namespace gw2v {
 
@@ -28,8 +29,10 @@ __device__ __forceinline__ void gk_red4(float* p, const float (&v)[4]) {
     atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
 }
 
-template <int G, int CHUNKS>
-__global__ void __launch_bounds__(GK_THREADS)
+// MINB = resident CTAs per SM the register allocation is capped for (short rows: 3 -> 80 registers,
+// 4 -> 64 registers with a few spills; long rows need the registers for the row data)
+template <int G, int CHUNKS, int MINB>
+__global__ void __launch_bounds__(GK_THREADS, MINB)
 sgns_fused_group_kernel(const SgnsParams p) {
     constexpr int P = 32 / G;
     __shared__ int ring_all[(GK_THREADS / 32) * GK_RING * PIPE_ENTRY];
@@ -160,24 +163,31 @@ bool sgns_group_supported(int K, int window, int negatives) {
     return K % 4 == 0 && K <= 1024;
 }
 
+static int gk_occ() {
+    static int occ = -1;
+    if (occ < 0) { const char* e = getenv("GW2V_GROUP_OCC"); occ = e ? atoi(e) : 3; }
+    return occ;
+}
+
 #define GW2V_GK_DISPATCH(K, CALL)                                            \
     do {                                                                     \
         int G_, ch_;                                                         \
         gk_group((K), &G_, &ch_);                                            \
-        if (G_ == 8) { CALL(8, 1); }                                         \
-        else if (G_ == 16) { CALL(16, 1); }                                  \
-        else if (ch_ == 1) { CALL(32, 1); }                                  \
-        else if (ch_ == 2) { CALL(32, 2); }                                  \
-        else if (ch_ == 3) { CALL(32, 3); }                                  \
-        else if (ch_ == 4) { CALL(32, 4); }                                  \
-        else if (ch_ <= 6) { CALL(32, 6); }                                  \
-        else { CALL(32, 8); }                                                \
+        const bool o4 = gk_occ() >= 4;                                       \
+        if (G_ == 8) { if (o4) CALL(8, 1, 4); else CALL(8, 1, 3); }          \
+        else if (G_ == 16) { if (o4) CALL(16, 1, 4); else CALL(16, 1, 3); }  \
+        else if (ch_ == 1) { if (o4) CALL(32, 1, 4); else CALL(32, 1, 3); }  \
+        else if (ch_ == 2) { CALL(32, 2, 2); }                               \
+        else if (ch_ == 3) { CALL(32, 3, 1); }                               \
+        else if (ch_ == 4) { CALL(32, 4, 1); }                               \
+        else if (ch_ <= 6) { CALL(32, 6, 1); }                               \
+        else { CALL(32, 8, 1); }                                             \
     } while (0)
 
 int sgns_group_grid(int K, int device) {
     int sms = 148, occ = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-#define CALL(GG, C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_fused_group_kernel<GG, C>, GK_THREADS, 0)
+#define CALL(GG, C, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_fused_group_kernel<GG, C, MB>, GK_THREADS, 0)
     GW2V_GK_DISPATCH(K, CALL);
 #undef CALL
     if (occ < 1) occ = 1;
@@ -185,7 +195,7 @@ int sgns_group_grid(int K, int device) {
 }
 
 void launch_sgns_group(const SgnsParams& p, int grid, cudaStream_t stream) {
-#define CALL(GG, C) sgns_fused_group_kernel<GG, C><<<grid, GK_THREADS, 0, stream>>>(p)
+#define CALL(GG, C, MB) sgns_fused_group_kernel<GG, C, MB><<<grid, GK_THREADS, 0, stream>>>(p)
     GW2V_GK_DISPATCH(p.K, CALL);
 #undef CALL
 }

@@ -44,7 +44,7 @@ struct GmWarpSmem {
 };
 
 template <int G, int CHUNKS>
-__global__ void __launch_bounds__(GM_THREADS)
+__global__ void __launch_bounds__(GM_THREADS, (CHUNKS == 1) ? 3 : ((CHUNKS == 2) ? 2 : 1))
 sgns_fused_group_multi_kernel(const SgnsParams p, uint32_t* warp_seq) {
     constexpr int P = 32 / G;
     __shared__ __align__(16) GmWarpSmem wsm[GM_THREADS / 32];

@@ -1,0 +1,476 @@
+// sgns_pairs: the SGNS training step over a pre-generated pair-descriptor array (pairgen.cu).
+//
+// This is the production hot path: dotprod -> (all-reduce of the partial dots across the column
+// shards) -> sigmoid / learning rate -> adjust of the reference (MLLIB:417-429 + the Glint server
+// ops [G]), as ONE kernel per rank.
+//
+//   * purely pair-parallel: descriptor p = {centre word, context word, n negatives}; a GROUP of
+//     G = 8/16/32 lanes owns a pair (G * 4 * CHUNKS >= K columns), a warp handles 32/G pairs per
+//     step and walks the steps warp-strided -- no generation, no rings, few registers, so 24-48
+//     warps per SM hide the latency of the random row gathers;
+//   * rows move with 16-byte LDG.cg / RED.128 (L2 is the coherence point of the atomic updates);
+//   * the 8 dots of a pair are reduced by one transposed butterfly, each sigmoid evaluated once;
+//   * world > 1: every pair is visited twice.  Pass A computes the partial dots over this rank's
+//     columns and, every 4 pairs, lane j stores the batch straight into rank j's symmetric exchange
+//     slot over NVLink (st.global.v4 on a peer-mapped address) followed by st.release.sys of the
+//     batch sequence number.  Pass B runs 16 pairs behind: it polls the peers' flags (ld.volatile +
+//     one ld.acquire.sys), sums the S partials in fixed rank order (bit-identical coefficients on
+//     every rank -- the reference's coefficient broadcast disappears), re-reads the rows (L2 hits)
+//     and applies the updates.  Between A and B of a batch the warp keeps working on other pairs
+//     and 24+ other warps are resident, so the NVLink round trip is off the critical path.  The
+//     schedule is static per warp; sequence numbers persist across launches.  No NCCL on this path.
+#include "common.cuh"
+#include "sgns_params.h"
+#include <cstdio>
+#include <cstdlib>
+
+namespace gw2v {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_FP = 8;              // floats per pair in exchange slots (1 + n <= 8)
+constexpr int PK_BATCH = 4;           // pairs per batch: slot = 32 floats = 128 B
+constexpr int PK_LAG = 16;            // pairs between pass A and pass B
+constexpr int PK_NSLOT = 14;          // >= 2 * (batches in flight + 1)
+
+template <int G> __device__ __forceinline__ int pk_row_of_lane(int lane) {
+    const int lg = lane & (G - 1);
+    return ((lg / (G / 2)) & 1) * 4 + ((lg / (G / 4)) & 1) * 2 + ((lg / (G / 8)) & 1);
+}
+template <int G> __device__ __forceinline__ int pk_lane_of_row(int r) {
+    return ((r >> 2) & 1) * (G / 2) + ((r >> 1) & 1) * (G / 4) + (r & 1) * (G / 8);
+}
+// transposed butterfly over a group of G lanes: 8 values in, the lane keeps the total of row
+// pk_row_of_lane<G>(lane); same pairing order as a plain xor butterfly (bit-identical totals)
+template <int G>
+__device__ __forceinline__ float pk_reduce8(const float (&f)[8], int lane) {
+    float a[4];
+    const bool h1 = lane & (G / 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = h1 ? f[j] : f[j + 4];
+        const float keep = h1 ? f[j + 4] : f[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, G / 2);
+    }
+    float b[2];
+    const bool h2 = lane & (G / 4);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = h2 ? a[j] : a[j + 2];
+        const float keep = h2 ? a[j + 2] : a[j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, send, G / 4);
+    }
+    const bool h3 = lane & (G / 8);
+    const float send = h3 ? b[0] : b[1];
+    const float keep = h3 ? b[1] : b[0];
+    float c = keep + __shfl_xor_sync(0xffffffffu, send, G / 8);
+#pragma unroll
+    for (int o = G / 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+}
+
+__device__ __forceinline__ void pk_ld4(const float* p, float (&o)[4]) {
+    float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void pk_red4(float* p, const float (&v)[4]) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// descriptor words 0..11 -> row index of row r is word r + 1 (row 0 = context = word 1)
+struct PairDesc { int w[12]; };
+__device__ __forceinline__ void pk_load_desc(const int* __restrict__ desc, long long pair, int pd, PairDesc& d) {
+    const int4* e = reinterpret_cast<const int4*>(desc + (size_t)pair * pd);
+    const int4 a = __ldg(e), b = __ldg(e + 1);
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+    d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    if (pd > 8) { const int4 c = __ldg(e + 2); d.w[8] = c.x; d.w[9] = c.y; d.w[10] = c.z; d.w[11] = c.w; }
+    else { d.w[8] = d.w[9] = d.w[10] = d.w[11] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------ single shard
+template <int G, int CHUNKS, int MINB>
+__global__ void __launch_bounds__(PK_THREADS, MINB)
+sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr, const int pd) {
+    constexpr int P = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int K = p.K;
+    const int n = p.negatives;
+    const int grp = lane / G, lg = lane % G;
+    bool act[CHUNKS];
+    int coff[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) { coff[c] = (c * G + lg) * 4; act[c] = coff[c] < K; }
+    const long long n_pairs = *n_pairs_ptr;
+    const long long nsteps = (n_pairs + P - 1) / P;
+    const long long warp_global = ((long long)blockIdx.x * PK_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * PK_THREADS) >> 5;
+    float loss = 0.f, maxdot = 0.f;
+    const int myrow = pk_row_of_lane<G>(lane);
+    const bool owner = lg == pk_lane_of_row<G>(myrow);
+
+    for (long long step = warp_global; step < nsteps; step += n_warps) {
+        const long long pair = step * P + grp;
+        const bool gvalid = pair < n_pairs;
+        PairDesc d;
+        pk_load_desc(desc, gvalid ? pair : 0, pd, d);
+        const int ctok = d.w[1];
+        float* urow = p.syn0 + (size_t)d.w[0] * K;
+        float u[CHUNKS][4], du[CHUNKS][4];
+        float v[8][CHUNKS][4];
+        bool ract[8];
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+            for (int el = 0; el < 4; ++el) { u[c][el] = 0.f; du[c][el] = 0.f; }
+            if (gvalid && act[c]) pk_ld4(urow + coff[c], u[c]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            ract[r] = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                for (int el = 0; el < 4; ++el) v[r][c][el] = 0.f;
+                if (ract[r] && act[c] && !(p.debug & 4)) pk_ld4(p.syn1 + (size_t)d.w[r + 1] * K + coff[c], v[r][c]);
+            }
+        }
+        float f[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+                for (int el = 0; el < 4; ++el) s = fmaf(u[c][el], v[r][c][el], s);
+            f[r] = s;
+        }
+        const float ftot = pk_reduce8<G>(f, lane);
+        unsigned actmask = 0;                       // bit r: row r takes part (no runtime indexing of d.w)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) actmask |= ract[r] ? (1u << r) : 0u;
+        const bool myact = (actmask >> myrow) & 1u;
+        const float mylabel = (myrow == 0) ? 1.f : 0.f;
+        const float gmine = myact ? sgns_coeff(ftot, mylabel, p.alpha, p.max_grad) : 0.f;
+        if (p.compute_loss && myact && owner) {
+            loss += softplus_clipped(mylabel > 0.5f ? -ftot : ftot);
+            maxdot = fmaxf(maxdot, fabsf(ftot));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float g = __shfl_sync(0xffffffffu, gmine, pk_lane_of_row<G>(r), G);
+            if (!ract[r]) continue;
+            float* vrow = p.syn1 + (size_t)d.w[r + 1] * K;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                if (!act[c]) continue;
+                float gu[4];
+#pragma unroll
+                for (int el = 0; el < 4; ++el) {
+                    du[c][el] = fmaf(g, v[r][c][el], du[c][el]);
+                    gu[el] = g * u[c][el];
+                }
+                if (!(p.debug & 1)) pk_red4(vrow + coff[c], gu);
+            }
+        }
+        if (gvalid && !(p.debug & 2)) {
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c)
+                if (act[c]) pk_red4(urow + coff[c], du[c]);
+        }
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_pairs; }
+    if (p.compute_loss) {
+        loss = warp_sum(loss);
+        maxdot = warp_max(maxdot);
+        if (lane == 0) {
+            if (loss != 0.f) atomicAdd(p.stats + 1, loss);
+            atomicMax(reinterpret_cast<int*>(p.stats + 2), __float_as_int(maxdot));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ column shards
+struct PkWarpSmem {
+    float fdot[2 * PK_LAG * PK_FP];      // partial (then total) dots of the pairs between pass A and pass B
+    float xsum[8 * 32];                  // per-source copy of one batch for the ordered reduction
+};
+
+template <int G, int CHUNKS, int MINB>
+__global__ void __launch_bounds__(PK_THREADS, MINB)
+sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr,
+                        const int pd, uint32_t* warp_seq) {
+    constexpr int P = 32 / G;
+    constexpr int BS = PK_BATCH / P;           // steps per batch
+    constexpr int LAGS = PK_LAG / P;           // lag in steps
+    constexpr int RFS = 2 * LAGS;              // dot ring in steps (multiple of BS)
+    __shared__ __align__(16) PkWarpSmem wsm[PK_THREADS / 32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* fdot = wsm[warp].fdot;
+    float* xsum = wsm[warp].xsum;
+    const int K = p.K;
+    const int n = p.negatives;
+    const int S = p.world;
+    const int rank = p.rank;
+    const int grp = lane / G, lg = lane % G;
+    bool act[CHUNKS];
+    int coff[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) { coff[c] = (c * G + lg) * 4; act[c] = coff[c] < K; }
+    const long long n_pairs = *n_pairs_ptr;
+    const long long nsteps = (n_pairs + P - 1) / P;
+    const int gwarp = blockIdx.x * (PK_THREADS / 32) + warp;            // identical on every rank
+    const int n_warps = gridDim.x * (PK_THREADS / 32);
+    const int nk = (gwarp < nsteps) ? (int)((nsteps - gwarp + n_warps - 1) / n_warps) : 0;   // this warp's steps
+    const int myrow = pk_row_of_lane<G>(lane);
+    const bool owner = lg == pk_lane_of_row<G>(myrow);
+
+    const size_t slot_stride = 32;                                               // floats per (slot, source)
+    const size_t warp_x_base = (size_t)gwarp * PK_NSLOT * S * slot_stride;
+    uint32_t* my_flags = p.flags[rank] + (size_t)gwarp * S;
+    const uint32_t seq0 = warp_seq[gwarp];
+    float loss = 0.f, maxdot = 0.f;
+    unsigned long long wait_ns = 0;
+
+    for (int k = 0; k < nk + LAGS; ++k) {
+        if (k < nk) {
+            // ------------------------------------------------------------ pass A: partial dots of step k
+            const long long pair = ((long long)gwarp + (long long)k * n_warps) * P + grp;
+            const bool gvalid = pair < n_pairs;
+            PairDesc d;
+            pk_load_desc(desc, gvalid ? pair : 0, pd, d);
+            const int ctok = d.w[1];
+            float u[CHUNKS][4];
+            float v[8][CHUNKS][4];
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                for (int el = 0; el < 4; ++el) u[c][el] = 0.f;
+                if (gvalid && act[c]) pk_ld4(p.syn0 + (size_t)d.w[0] * K + coff[c], u[c]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const bool ra = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) v[r][c][el] = 0.f;
+                    if (ra && act[c]) pk_ld4(p.syn1 + (size_t)d.w[r + 1] * K + coff[c], v[r][c]);
+                }
+            }
+            float f[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) s = fmaf(u[c][el], v[r][c][el], s);
+                f[r] = s;
+            }
+            const float tot = pk_reduce8<G>(f, lane);
+            if (owner) fdot[((k % RFS) * P + grp) * PK_FP + myrow] = gvalid ? tot : 0.f;
+            if ((k + 1) % BS == 0 || k == nk - 1) {
+                // ---- push the batch: lane j -> rank j's slot, then release-publish the sequence number
+                __syncwarp();
+                const int b = k / BS;
+                const uint32_t bseq = seq0 + (uint32_t)b;
+                const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
+                if (lane < S && lane != rank) {
+                    float4* dst = reinterpret_cast<float4*>(p.xbuf[lane] + warp_x_base +
+                                                            ((size_t)slot * S + rank) * slot_stride);
+                    const float4* src = reinterpret_cast<const float4*>(fdot + (size_t)((b * BS) % RFS) * P * PK_FP);
+#pragma unroll
+                    for (int v4 = 0; v4 < 8; ++v4) dst[v4] = src[v4];
+                    st_release_sys(p.flags[lane] + (size_t)gwarp * S + rank, bseq + 1u);
+                }
+                __syncwarp();
+            }
+        }
+        const int kb = k - LAGS;
+        if (kb >= 0) {
+            // ------------------------------------------------------------ pass B: reduce + update step kb
+            if (kb % BS == 0) {
+                const int b = kb / BS;
+                const uint32_t bseq = seq0 + (uint32_t)b;
+                const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
+                float* mine = fdot + (size_t)((b * BS) % RFS) * P * PK_FP;       // 32 floats of this batch
+                if (lane < S && lane != rank) {
+                    unsigned long long t0 = p.timing ? globaltimer_ns() : 0ull;
+                    uint32_t spins = 0;
+                    volatile uint32_t* fl = my_flags + lane;
+                    while ((int32_t)(*fl - (bseq + 1u)) < 0) {
+                        if ((++spins & 0x3FFFu) == 0) {
+                            if (t0 == 0ull) t0 = globaltimer_ns();
+                            if (globaltimer_ns() - t0 > 20000000000ull) {
+                                printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u (flag %u)\n",
+                                       rank, gwarp, lane, bseq + 1u, *fl);
+                                atomicExch(p.error_flag, 1);
+                                __trap();
+                            }
+                        }
+                    }
+                    (void)ld_acquire_sys(my_flags + lane);      // acquire: the peer's data stores are visible
+                    if (p.timing) wait_ns += globaltimer_ns() - t0;
+                    const float4* src = reinterpret_cast<const float4*>(
+                        p.xbuf[rank] + warp_x_base + ((size_t)slot * S + lane) * slot_stride);
+                    float4 got[8];
+#pragma unroll
+                    for (int v4 = 0; v4 < 8; ++v4) got[v4] = __ldcg(src + v4);
+#pragma unroll
+                    for (int v4 = 0; v4 < 8; ++v4) reinterpret_cast<float4*>(xsum + lane * 32)[v4] = got[v4];
+                }
+                xsum[rank * 32 + lane] = mine[lane];
+                __syncwarp();
+                float tot = 0.f;
+                for (int r = 0; r < S; ++r) tot += xsum[r * 32 + lane];      // fixed order: bit-identical on all ranks
+                mine[lane] = tot;
+                __syncwarp();
+            }
+            const long long pair = ((long long)gwarp + (long long)kb * n_warps) * P + grp;
+            const bool gvalid = pair < n_pairs;
+            PairDesc d;
+            pk_load_desc(desc, gvalid ? pair : 0, pd, d);
+            const int ctok = d.w[1];
+            float* urow = p.syn0 + (size_t)d.w[0] * K;
+            float u[CHUNKS][4], du[CHUNKS][4];
+            float v[8][CHUNKS][4];
+            bool ract[8];
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                for (int el = 0; el < 4; ++el) { u[c][el] = 0.f; du[c][el] = 0.f; }
+                if (gvalid && act[c]) pk_ld4(urow + coff[c], u[c]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                ract[r] = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) v[r][c][el] = 0.f;
+                    if (ract[r] && act[c]) pk_ld4(p.syn1 + (size_t)d.w[r + 1] * K + coff[c], v[r][c]);
+                }
+            }
+            const float fm = fdot[((kb % RFS) * P + grp) * PK_FP + myrow];
+            unsigned actmask = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) actmask |= ract[r] ? (1u << r) : 0u;
+            const bool myact = (actmask >> myrow) & 1u;
+            const float mylabel = (myrow == 0) ? 1.f : 0.f;
+            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad) : 0.f;
+            if (p.compute_loss && myact && owner) {
+                loss += softplus_clipped(mylabel > 0.5f ? -fm : fm);
+                maxdot = fmaxf(maxdot, fabsf(fm));
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float g = __shfl_sync(0xffffffffu, gmine, pk_lane_of_row<G>(r), G);
+                if (!ract[r]) continue;
+                float* vrow = p.syn1 + (size_t)d.w[r + 1] * K;
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    if (!act[c]) continue;
+                    float gu[4];
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) {
+                        du[c][el] = fmaf(g, v[r][c][el], du[c][el]);
+                        gu[el] = g * u[c][el];
+                    }
+                    if (!(p.debug & 1)) pk_red4(vrow + coff[c], gu);
+                }
+            }
+            if (gvalid && !(p.debug & 2)) {
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c)
+                    if (act[c]) pk_red4(urow + coff[c], du[c]);
+            }
+        }
+    }
+    if (lane == 0) warp_seq[gwarp] = seq0 + (uint32_t)((nk + BS - 1) / BS);
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_pairs; }
+    if (p.compute_loss) {
+        loss = warp_sum(loss);
+        maxdot = warp_max(maxdot);
+        if (lane == 0) {
+            if (loss != 0.f) atomicAdd(p.stats + 1, loss);
+            atomicMax(reinterpret_cast<int*>(p.stats + 2), __float_as_int(maxdot));
+        }
+    }
+    if (p.timing) {
+        unsigned long long w = 0;
+        for (int o = 0; o < 32; ++o) { unsigned long long x = __shfl_sync(0xffffffffu, wait_ns, o); w = x > w ? x : w; }
+        if (lane == 0 && w) atomicAdd(p.timing + 0, w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static void pk_group(int K, int* G, int* chunks) {
+    if (K <= 32) { *G = 8; *chunks = 1; }
+    else if (K <= 64) { *G = 16; *chunks = 1; }
+    else { *G = 32; *chunks = (K + 127) / 128; }
+}
+
+bool sgns_pairs_supported(int K, int window, int negatives) {
+    return negatives >= 1 && negatives <= 7 && window >= 1 && window <= 11 && K % 4 == 0 && K <= 1024;
+}
+
+static int pk_occ() {
+    static int occ = -1;
+    if (occ < 0) { const char* e = getenv("GW2V_PAIRS_OCC"); occ = e ? atoi(e) : 3; }
+    return occ;
+}
+
+#define GW2V_PK_DISPATCH(K, CALL)                                            \
+    do {                                                                     \
+        int G_, ch_;                                                         \
+        pk_group((K), &G_, &ch_);                                            \
+        const bool o4 = pk_occ() >= 4;                                       \
+        if (G_ == 8) { if (o4) CALL(8, 1, 4); else CALL(8, 1, 3); }          \
+        else if (G_ == 16) { if (o4) CALL(16, 1, 4); else CALL(16, 1, 3); }  \
+        else if (ch_ == 1) { if (o4) CALL(32, 1, 4); else CALL(32, 1, 3); }  \
+        else if (ch_ == 2) { CALL(32, 2, 2); }                               \
+        else if (ch_ == 3) { CALL(32, 3, 1); }                               \
+        else if (ch_ == 4) { CALL(32, 4, 1); }                               \
+        else if (ch_ <= 6) { CALL(32, 6, 1); }                               \
+        else { CALL(32, 8, 1); }                                             \
+    } while (0)
+
+int sgns_pairs_grid(int K, int device, bool multi) {
+    int sms = 148, occ = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (multi) {
+#define CALL(GG, C, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB>, PK_THREADS, 0)
+        GW2V_PK_DISPATCH(K, CALL);
+#undef CALL
+    } else {
+#define CALL(GG, C, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_kernel<GG, C, MB>, PK_THREADS, 0)
+        GW2V_PK_DISPATCH(K, CALL);
+#undef CALL
+    }
+    if (occ < 1) occ = 1;
+    return sms * occ;               // multi: every CTA co-resident, required by the in-kernel flag protocol
+}
+
+void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats) {
+    *warps_per_cta = PK_THREADS / 32;
+    *nslot = PK_NSLOT;
+    *slot_floats = 32;
+}
+
+void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid, cudaStream_t stream) {
+#define CALL(GG, C, MB) sgns_pairs_kernel<GG, C, MB><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd)
+    GW2V_PK_DISPATCH(p.K, CALL);
+#undef CALL
+}
+
+void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
+                             uint32_t* warp_seq, cudaStream_t stream) {
+#define CALL(GG, C, MB) sgns_pairs_multi_kernel<GG, C, MB><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq)
+    GW2V_PK_DISPATCH(p.K, CALL);
+#undef CALL
+}
+
+}  // namespace gw2v

@@ -48,6 +48,14 @@ bool sgns_pipe_supported(int K, int window, int negatives);
 int sgns_pipe_grid(int K, int negatives, int device);
 void launch_sgns_pipe(const SgnsParams& p, int grid, cudaStream_t stream);
 
+// sgns_pairs.cu: production step over pre-generated pair descriptors (pairgen.cu)
+bool sgns_pairs_supported(int K, int window, int negatives);
+int sgns_pairs_grid(int K, int device, bool multi);
+void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats);
+void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid, cudaStream_t stream);
+void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
+                             uint32_t* warp_seq, cudaStream_t stream);
+
 // sgns_group.cu: register-path kernel with lane groups (short rows / high occupancy)
 bool sgns_group_supported(int K, int window, int negatives);
 int sgns_group_grid(int K, int device);

@@ -48,6 +48,7 @@ class CudaShardOps:
         self.subsample_active = True
         self._cap = 0
         self._epoch = 0
+        self._pg_epoch = 0
         self._stats_ring = None
         self._stats_i = 0
         self._xchg = None
@@ -93,6 +94,15 @@ class CudaShardOps:
         self.pin_sid = torch.empty(cap, dtype=torch.int32).pin_memory()
         self._stats_ring = torch.zeros(256, 4, dtype=torch.float32, device=d)
         self._count_val = -1
+        # pair-generation workspaces (pairgen.cu)
+        cfg = self.cfg
+        self.pd = int(_C.pairgen_desc_ints(cfg.negatives))
+        self.pg_cinfo = torch.empty(cap, dtype=torch.int32, device=d)
+        self.pg_off = torch.empty(cap, dtype=torch.int32, device=d)
+        self.pg_npairs = torch.zeros(1, dtype=torch.int32, device=d)
+        self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd, dtype=torch.int32, device=d)
+        self.pg_ticket = torch.zeros(1, dtype=torch.int32, device=d)
+        self.pg_chain = torch.zeros(int(_C.pairgen_max_blocks(cap)) + 1, dtype=torch.int64, device=d)
         self._cap = cap
 
     # ------------------------------------------------------------------ cross-shard exchange
@@ -104,10 +114,19 @@ class CudaShardOps:
         want = os.environ.get("GW2V_MULTI_KERNEL", "auto")
         pipe_ok = bool(_C.sgns_pipe_multi_supported(self.K, cfg.window, cfg.negatives))
         group_ok = bool(_C.sgns_group_multi_supported(self.K, cfg.window, cfg.negatives))
+        pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))
         if want == "auto":
-            want = "group" if group_ok else ("pipe" if pipe_ok else "v1")
-        variant = 2 if (want == "group" and group_ok) else (1 if (want == "pipe" and pipe_ok) else 0)
-        if variant >= 1:
+            want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
+        variant = 3 if (want == "pairs" and pairs_ok) else (
+            2 if (want == "group" and group_ok) else (1 if (want == "pipe" and pipe_ok) else 0))
+        if variant == 3:
+            grid = int(_C.sgns_pairs_grid(self.K, dev_index, True))
+            warps, nslot, slot_floats = [int(x) for x in _C.sgns_pairs_multi_geometry()]
+            tb = 0
+            units = grid * warps
+            xbytes = units * nslot * self.world * slot_floats * 4
+            nseq = units
+        elif variant >= 1:
             geo = _C.sgns_group_multi_geometry(self.K, dev_index) if variant == 2 else \
                 _C.sgns_pipe_multi_geometry(self.K, cfg.negatives, dev_index)
             grid, warps, nslot, slot_floats = [int(x) for x in geo]
@@ -187,7 +206,17 @@ class CudaShardOps:
         stats = self._stats_ring[self._stats_i]
         stats.zero_()
         wm = WINDOW_MODES[cfg.window_mode]
-        if self.world > 1:
+        if self.world > 1 and self._xchg["variant"] == 3:
+            x = self._xchg
+            self._pg_epoch += 1
+            _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                               int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                               float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank,
+                               x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
+                               self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_ticket,
+                               self.pg_chain, self._pg_epoch)
+            self.launches += 2
+        elif self.world > 1:
             x = self._xchg
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
@@ -197,6 +226,15 @@ class CudaShardOps:
         else:
             if not hasattr(self, "_grid1"):
                 self._variant, self._grid1 = self._pick_single_kernel()
+            if self._variant == 3:
+                self._pg_epoch += 1
+                _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                                   int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                                   float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
+                                   None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
+                                   self.pg_ticket, self.pg_chain, self._pg_epoch)
+                self.launches += 3
+                return stats
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
@@ -211,10 +249,13 @@ class CudaShardOps:
         want = os.environ.get("GW2V_SINGLE_KERNEL", "auto")
         group_ok = bool(_C.sgns_group_supported(self.K, cfg.window, cfg.negatives))
         pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
+        pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))
         if want == "auto":
             # measured on B200 (profiles/r1_kernel_variants.md): the lane-group register path wins at every
             # row length (TMA bulk copies cost ~25 SM cycles each, which binds the pipeline for short rows)
-            want = "group" if group_ok else ("pipe" if pipe_ok else "v1")
+            want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
+        if want == "pairs" and pairs_ok:
+            return 3, int(_C.sgns_pairs_grid(self.K, dev_index, False))
         if want == "group" and group_ok:
             return 2, int(_C.sgns_group_grid(self.K, dev_index))
         if want == "pipe" and pipe_ok:
