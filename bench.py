@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=131072, help="tokens (centre words) per step, global")
     ap.add_argument("--sent-len", type=int, default=1000)
     ap.add_argument("--zipf", type=float, default=1.0)
-    ap.add_argument("--subsample", default="reference", choices=["reference", "word2vec"])
+    ap.add_argument("--subsample", default="word2vec", choices=["reference", "word2vec"],
+                    help="word2vec = the intended formula of MLLIB:375-377 at --subsample-ratio; reference = the "
+                         "reference's effective behaviour (integer-division bug: nothing is dropped)")
     ap.add_argument("--subsample-ratio", type=float, default=1e-4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lr", type=float, default=0.025)
@@ -231,7 +233,9 @@ def main():
     result["config"] = {
         "model": "SGNS word2vec", "vocab": args.vocab, "dim": args.dim, "neg": args.neg, "window": args.window,
         "global_batch": B, "seq_len": args.sent_len, "parallelism": f"column-shard x{world}",
-        "cols_per_gpu": eng.shard.cols, "window_mode": cfg.window_mode, "subsample": args.subsample,
+        "cols_per_gpu": eng.shard.cols, "window_mode": cfg.window_mode,
+        "subsample": args.subsample + (" t=%g" % args.subsample_ratio if args.subsample == "word2vec" else " (inert)"),
+        "pairs_counted": "trained (centre, context) pairs after sub-sampling",
         "neg_sharing": "pair (n private negatives per (centre, context) pair)",
         "l2": "inputs (2 x %.1f GB embedding shards per GPU) far larger than the 126 MB L2; no flush needed"
               % (args.vocab * eng.shard.cols * 4 / 1e9),

@@ -111,6 +111,7 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     TORCH_CHECK(cinfo.numel() >= max_tokens && pair_off.numel() >= max_tokens, "pairgen workspaces too small");
     TORCH_CHECK(desc.numel() >= max_tokens * 2 * window * pd, "descriptor buffer too small");
     TORCH_CHECK(chain.numel() >= gw2v::pairgen_max_blocks((int)max_tokens), "chain buffer too small");
+    TORCH_CHECK(max_tokens <= gw2v::pairgen_max_tokens(), "step too large for the pair generator (max ", gw2v::pairgen_max_tokens(), " tokens)");
     c10::cuda::CUDAGuard guard(syn0.device());
     gw2v::SgnsParams p{};
     p.syn0 = syn0.data_ptr<float>();

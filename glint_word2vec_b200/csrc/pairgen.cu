@@ -7,10 +7,12 @@
 // ~40 registers; as separate, embarrassingly parallel kernels it is a few microseconds per step and
 // the training kernels become purely pair-parallel (any warp can take any pair).
 //
-//   pair_count_scan : one thread per centre: window radius (Philox), valid-context bitmask, pair
-//                     count; single-pass chained block scan -> exclusive offsets + total
+//   pair_count      : one thread per centre: window radius (Philox), valid-context bitmask, pair
+//                     count, exclusive offset inside the 1024-centre tile, tile sums
+//   pair_tile_scan  : one CTA scans the (<= 1024) tile sums and writes the total pair count
 //   pair_fill       : one thread per (centre, offset slot): descriptor {centre word, context word,
-//                     negatives[n]} at offset[centre] + rank
+//                     negatives[n]} at tile_prefix + offset[centre] + rank
+// (a single-pass chained scan was measured first: its serial CTA-to-CTA hand-off cost ~100 us per step)
 // All decisions are bit-identical to models/sgns.py (enumerate_pairs / draw_negatives).
 #include "common.cuh"
 #include "launchers.h"
@@ -22,20 +24,16 @@ constexpr int PC_ITEMS = 4;
 constexpr int PC_TILE = PC_THREADS * PC_ITEMS;
 
 // cinfo[i] = valid-context bitmask (bits 0..23, bit q <-> offset lo + q) | (-lo) << 24
+// pair_off[i] = exclusive offset of centre i INSIDE its tile; tile_sum[b] = pairs of tile b
 __global__ void __launch_bounds__(PC_THREADS)
-pair_count_scan_kernel(const int* __restrict__ tokens, const int* __restrict__ sent_id, const int* __restrict__ n_tokens,
-                       uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
-                       int window, int window_mode, uint32_t* __restrict__ cinfo, int* __restrict__ pair_off,
-                       int* __restrict__ n_pairs, unsigned int* ticket, unsigned long long* chain, uint32_t epoch) {
-    __shared__ unsigned int bid_s;
+pair_count_kernel(const int* __restrict__ tokens, const int* __restrict__ sent_id, const int* __restrict__ n_tokens,
+                  uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
+                  int window, int window_mode, uint32_t* __restrict__ cinfo, int* __restrict__ pair_off,
+                  int* __restrict__ tile_sum) {
     __shared__ int warp_tot[PC_THREADS / 32];
-    __shared__ int base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = *n_tokens;
-    if (tid == 0) bid_s = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned int bid = bid_s;
-    const int start = (int)bid * PC_TILE + tid * PC_ITEMS;
+    const int start = (int)blockIdx.x * PC_TILE + tid * PC_ITEMS;
     const uint32_t sw = stream_word(STREAM_WINDOW, iteration);
 
     int cnt[PC_ITEMS];
@@ -74,26 +72,10 @@ pair_count_scan_kernel(const int* __restrict__ tokens, const int* __restrict__ s
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
         if (lane < PC_THREADS / 32) warp_tot[lane] = xs - w;
-        if (lane == PC_THREADS / 32 - 1) {
-            const int block_total = xs;
-            unsigned long long prev = 0;
-            if (bid > 0) {
-                volatile unsigned long long* c = chain + (bid - 1);
-                unsigned long long v;
-                do { v = *c; } while ((uint32_t)(v >> 32) != epoch);
-                prev = v & 0xFFFFFFFFull;
-            }
-            base_s = (int)prev;
-            __threadfence();
-            atomicExch(chain + bid, ((unsigned long long)epoch << 32) | (prev + (unsigned long long)block_total));
-            if (bid == gridDim.x - 1) {
-                *n_pairs = (int)(prev + block_total);
-                *ticket = 0u;
-            }
-        }
+        if (lane == PC_THREADS / 32 - 1) tile_sum[blockIdx.x] = xs;
     }
     __syncthreads();
-    int o = base_s + warp_tot[warp] + (x - local);
+    int o = warp_tot[warp] + (x - local);
 #pragma unroll
     for (int e = 0; e < PC_ITEMS; ++e) {
         const int i = start + e;
@@ -102,9 +84,33 @@ pair_count_scan_kernel(const int* __restrict__ tokens, const int* __restrict__ s
     }
 }
 
+// exclusive scan of the (<= 1024) tile sums by one CTA; writes the total pair count
+__global__ void __launch_bounds__(1024)
+pair_tile_scan_kernel(int* __restrict__ tile_sum, int ntiles, int* __restrict__ n_pairs) {
+    __shared__ int wt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int v = tid < ntiles ? tile_sum[tid] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wt[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wt[lane];
+        int xs = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
+        wt[lane] = xs - w;
+        if (lane == 31) *n_pairs = xs;
+    }
+    __syncthreads();
+    if (tid < ntiles) tile_sum[tid] = wt[warp] + x - v;          // exclusive prefix of tile tid
+}
+
 // one thread per (centre, offset slot q); PD ints per descriptor: {wtok, ctok, negs[n], pad}
 __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __restrict__ n_tokens,
                                  const uint32_t* __restrict__ cinfo, const int* __restrict__ pair_off,
+                                 const int* __restrict__ tile_prefix,
                                  const int2* __restrict__ alias, int vocab, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t iteration, unsigned long long pos0, int window, int negatives, int slots,
                                  int pd, int* __restrict__ desc) {
@@ -119,7 +125,7 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     const int lo = -(int)(info >> 24);
     const int off = lo + q;
     const int rank = __popc(mask & ((1u << q) - 1u));
-    int* e = desc + (size_t)(__ldg(pair_off + i) + rank) * pd;
+    int* e = desc + (size_t)(__ldg(tile_prefix + (int)(i / PC_TILE)) + __ldg(pair_off + i) + rank) * pd;
     const int ctok = __ldg(tokens + i + off);
     e[0] = __ldg(tokens + i);
     e[1] = ctok;
@@ -135,24 +141,28 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
 
 int pairgen_max_blocks(int max_tokens) { return (max_tokens + PC_TILE - 1) / PC_TILE + 1; }
 int pairgen_desc_ints(int negatives) { return ((2 + negatives) + 3) / 4 * 4; }
+int pairgen_max_tokens() { return 1024 * PC_TILE; }
 
 // grid is sized from the host-side upper bound `max_tokens` (the device count may be smaller after
-// sub-sampling); blocks beyond the device count contribute zero pairs.
+// sub-sampling); tiles beyond the device count contribute zero pairs.  Three launches, no serial chain:
+// per-tile counts + local offsets -> scan of the tile sums -> descriptor fill.
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
                     int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, unsigned int* ticket, unsigned long long* chain, uint32_t epoch, cudaStream_t stream) {
+                    int* desc, unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
+                    cudaStream_t stream) {
     if (max_tokens <= 0) { cudaMemsetAsync(n_pairs, 0, sizeof(int), stream); return; }
-    const int grid = (max_tokens + PC_TILE - 1) / PC_TILE;
-    pair_count_scan_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration,
-                                                            pos0, window, window_mode, cinfo, pair_off, n_pairs,
-                                                            ticket, chain, epoch);
+    const int grid = (max_tokens + PC_TILE - 1) / PC_TILE;          // <= 1024 (checked by the binding)
+    int* tile_sum = reinterpret_cast<int*>(chain);                   // reuse the workspace: >= grid ints
+    pair_count_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration, pos0,
+                                                       window, window_mode, cinfo, pair_off, tile_sum);
+    pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, n_pairs);
     const int slots = 2 * window + 1;
     const long long total = (long long)max_tokens * slots;
-    pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, alias,
-                                                                         vocab, seed_lo, seed_hi, iteration, pos0,
-                                                                         window, negatives, slots, pairgen_desc_ints(negatives),
-                                                                         desc);
+    pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, tile_sum,
+                                                                         alias, vocab, seed_lo, seed_hi, iteration,
+                                                                         pos0, window, negatives, slots,
+                                                                         pairgen_desc_ints(negatives), desc);
 }
 
 }  // namespace gw2v

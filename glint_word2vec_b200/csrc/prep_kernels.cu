@@ -1,7 +1,7 @@
 // Pre-processing kernels (SURVEY.md 2.5 K6, K14 + weight init):
 //   subsample_compact : frequent-word sub-sampling (MLLIB:371-379) as an
-//                       order-preserving stream compaction (single pass,
-//                       chained block scan), sentence ids ride along.
+//                       order-preserving stream compaction (count / tile scan /
+//                       scatter), sentence ids ride along.
 //   zipf_stream       : synthetic Zipf token stream from the alias table.
 //   init_syn0         : syn0 ~ U(-0.5,0.5)/d as a pure function of (row, col).
 // Windowing (K7) and negative sampling (K5) are fused into sgns_fused.
@@ -14,23 +14,73 @@ constexpr int SC_THREADS = 256;
 constexpr int SC_ITEMS = 8;
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
-// chain[b] = (epoch << 32) | inclusive prefix of blocks 0..b
-__global__ void __launch_bounds__(SC_THREADS)
-subsample_compact_kernel(const int* __restrict__ tok_in, const int* __restrict__ sid_in, int T,
-                         const uint32_t* __restrict__ keep_thresh, uint32_t seed_lo, uint32_t seed_hi,
-                         uint32_t iteration, unsigned long long raw_pos0, int* __restrict__ tok_out,
-                         int* __restrict__ sid_out, int* __restrict__ count_out,
-                         unsigned int* ticket, unsigned long long* chain, uint32_t epoch) {
-    __shared__ unsigned int bid_s;
-    __shared__ int warp_tot[SC_THREADS / 32];
-    __shared__ int base_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) bid_s = atomicAdd(ticket, 1u);       // dynamic block id: predecessors are running
-    __syncthreads();
-    const unsigned int bid = bid_s;
-    const int start = (int)bid * SC_TILE + tid * SC_ITEMS;
-    const uint32_t sw = stream_word(STREAM_SUBSAMPLE, iteration);
+__device__ __forceinline__ bool sc_keep(const int* __restrict__ tok_in, const uint32_t* __restrict__ keep_thresh,
+                                        uint32_t seed_lo, uint32_t seed_hi, uint32_t sw, unsigned long long raw_pos0,
+                                        int i, int& tok) {
+    tok = __ldg(tok_in + i);
+    uint4 r = rand4(seed_lo, seed_hi, sw, raw_pos0 + (unsigned long long)i, 0u);
+    return r.x <= __ldg(keep_thresh + tok);
+}
 
+// pass 1: kept tokens per tile
+__global__ void __launch_bounds__(SC_THREADS)
+subsample_count_kernel(const int* __restrict__ tok_in, int T, const uint32_t* __restrict__ keep_thresh,
+                       uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long raw_pos0,
+                       int* __restrict__ tile_sum) {
+    __shared__ int wt[SC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int start = (int)blockIdx.x * SC_TILE + tid * SC_ITEMS;
+    const uint32_t sw = stream_word(STREAM_SUBSAMPLE, iteration);
+    int local = 0;
+#pragma unroll
+    for (int e = 0; e < SC_ITEMS; ++e) {
+        const int i = start + e;
+        int tok;
+        if (i < T && sc_keep(tok_in, keep_thresh, seed_lo, seed_hi, sw, raw_pos0, i, tok)) ++local;
+    }
+    local = (int)warp_sum((float)local);           // counts <= 256: exact in fp32
+    if (lane == 0) wt[warp] = local;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int w = 0; w < SC_THREADS / 32; ++w) s += wt[w];
+        tile_sum[blockIdx.x] = s;
+    }
+}
+
+// pass 2: one CTA turns the (<= 1024) tile sums into exclusive prefixes and writes the total
+__global__ void __launch_bounds__(1024)
+subsample_tile_scan_kernel(int* __restrict__ tile_sum, int ntiles, int* __restrict__ count_out) {
+    __shared__ int wt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int v = tid < ntiles ? tile_sum[tid] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wt[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wt[lane];
+        int xs = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
+        wt[lane] = xs - w;
+        if (lane == 31) *count_out = xs;
+    }
+    __syncthreads();
+    if (tid < ntiles) tile_sum[tid] = wt[warp] + x - v;
+}
+
+// pass 3: order-preserving scatter (decisions recomputed, identical by construction)
+__global__ void __launch_bounds__(SC_THREADS)
+subsample_scatter_kernel(const int* __restrict__ tok_in, const int* __restrict__ sid_in, int T,
+                         const uint32_t* __restrict__ keep_thresh, uint32_t seed_lo, uint32_t seed_hi,
+                         uint32_t iteration, unsigned long long raw_pos0, const int* __restrict__ tile_prefix,
+                         int* __restrict__ tok_out, int* __restrict__ sid_out) {
+    __shared__ int warp_tot[SC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int start = (int)blockIdx.x * SC_TILE + tid * SC_ITEMS;
+    const uint32_t sw = stream_word(STREAM_SUBSAMPLE, iteration);
     int tok[SC_ITEMS];
     bool keep[SC_ITEMS];
     int local = 0;
@@ -39,13 +89,10 @@ subsample_compact_kernel(const int* __restrict__ tok_in, const int* __restrict__
         const int i = start + e;
         keep[e] = false; tok[e] = 0;
         if (i < T) {
-            tok[e] = __ldg(tok_in + i);
-            uint4 r = rand4(seed_lo, seed_hi, sw, raw_pos0 + (unsigned long long)i, 0u);
-            keep[e] = r.x <= __ldg(keep_thresh + tok[e]);
+            keep[e] = sc_keep(tok_in, keep_thresh, seed_lo, seed_hi, sw, raw_pos0, i, tok[e]);
             local += keep[e] ? 1 : 0;
         }
     }
-    // block exclusive scan of `local`
     int x = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -56,28 +103,10 @@ subsample_compact_kernel(const int* __restrict__ tok_in, const int* __restrict__
         int xs = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
-        if (lane < SC_THREADS / 32) warp_tot[lane] = xs - w;       // exclusive warp offsets
-        if (lane == SC_THREADS / 32 - 1) {
-            const int block_total = xs;
-            // chained scan: wait for the predecessor's inclusive prefix of this epoch
-            unsigned long long prev = 0;
-            if (bid > 0) {
-                volatile unsigned long long* c = chain + (bid - 1);
-                unsigned long long v;
-                do { v = *c; } while ((uint32_t)(v >> 32) != epoch);
-                prev = v & 0xFFFFFFFFull;
-            }
-            base_s = (int)prev;
-            __threadfence();
-            atomicExch(chain + bid, ((unsigned long long)epoch << 32) | (prev + (unsigned long long)block_total));
-            if (bid == gridDim.x - 1) {            // last tile: publish the count, re-arm the ticket
-                *count_out = (int)(prev + block_total);
-                *ticket = 0u;
-            }
-        }
+        if (lane < SC_THREADS / 32) warp_tot[lane] = xs - w;
     }
     __syncthreads();
-    int o = base_s + warp_tot[warp] + (x - local);
+    int o = tile_prefix[blockIdx.x] + warp_tot[warp] + (x - local);
 #pragma unroll
     for (int e = 0; e < SC_ITEMS; ++e) {
         if (keep[e]) {
@@ -88,16 +117,20 @@ subsample_compact_kernel(const int* __restrict__ tok_in, const int* __restrict__
     }
 }
 
+// three launches, no CTA-to-CTA chain (a single-pass chained scan cost ~100 us per step on B200)
 void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const uint32_t* keep_thresh,
                               uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration,
                               unsigned long long raw_pos0, int* tok_out, int* sid_out, int* count_out,
-                              unsigned int* ticket, unsigned long long* chain, uint32_t epoch,
+                              unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
                               cudaStream_t stream) {
     if (T <= 0) { cudaMemsetAsync(count_out, 0, sizeof(int), stream); return; }
-    int grid = (T + SC_TILE - 1) / SC_TILE;
-    subsample_compact_kernel<<<grid, SC_THREADS, 0, stream>>>(tok_in, sid_in, T, keep_thresh, seed_lo, seed_hi,
-                                                              iteration, raw_pos0, tok_out, sid_out, count_out,
-                                                              ticket, chain, epoch);
+    const int grid = (T + SC_TILE - 1) / SC_TILE;                  // <= 1024 tiles (2M tokens per step)
+    int* tile_sum = reinterpret_cast<int*>(chain);
+    subsample_count_kernel<<<grid, SC_THREADS, 0, stream>>>(tok_in, T, keep_thresh, seed_lo, seed_hi, iteration,
+                                                            raw_pos0, tile_sum);
+    subsample_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, count_out);
+    subsample_scatter_kernel<<<grid, SC_THREADS, 0, stream>>>(tok_in, sid_in, T, keep_thresh, seed_lo, seed_hi,
+                                                              iteration, raw_pos0, tile_sum, tok_out, sid_out);
 }
 
 int subsample_max_blocks(int max_tokens) { return (max_tokens + SC_TILE - 1) / SC_TILE + 1; }

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from ..data.corpus import EncodedCorpus, iter_steps
+from ..utils.tracing import nvtx_range
 from . import sgns
 from .engine import ShardEngine
 
@@ -90,7 +91,8 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
                 words_it += batch.n_words
                 continue
             alpha = sgns.learning_rate(learning_rate, words_prev + words_it, total_words)
-            stats = engine.train_step(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
+            with nvtx_range("sgns_step"):
+                stats = engine.train_step(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
             pending.append(stats)
             words_it += batch.n_words
             rep.steps += 1

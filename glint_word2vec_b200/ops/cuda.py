@@ -194,7 +194,7 @@ class CudaShardOps:
             _C.subsample_compact(tok_dev, sid_dev, t, self.keep_dev, int(cfg.seed), int(iteration),
                                  int(raw_pos0), self.tok_c, self.sid_c, self.count, self.ticket, self.chain,
                                  self._epoch)
-            self.launches += 1
+            self.launches += 3            # count, tile scan, scatter
             self._count_val = -1
             tok, sid = self.tok_c, self.sid_c
         else:
@@ -215,7 +215,7 @@ class CudaShardOps:
                                x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
                                self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_ticket,
                                self.pg_chain, self._pg_epoch)
-            self.launches += 2
+            self.launches += 3            # + the training kernel counted below
         elif self.world > 1:
             x = self._xchg
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
@@ -233,7 +233,7 @@ class CudaShardOps:
                                    float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
                                    None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
                                    self.pg_ticket, self.pg_chain, self._pg_epoch)
-                self.launches += 3
+                self.launches += 4            # pair_count, pair_tile_scan, pair_fill, sgns_pairs
                 return stats
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
