@@ -5,7 +5,13 @@ for one 8xB200 NVSwitch box: column-sharded embedding matrices, a fused
 sm_100a dotprod -> all-reduce -> adjust kernel, and the Spark-ML style
 ``ServerSideGlintWord2Vec`` / ``ServerSideGlintWord2VecModel`` API.
 """
+import os as _os
+
 __version__ = "0.1.0"
+
+if _os.environ.get("GW2V_LOG_CONFIG"):
+    from .utils.logconfig import configure_logging as _configure_logging
+    _configure_logging()
 
 _LAZY = {
     "ServerSideGlintWord2Vec": ".api.estimator",

@@ -20,7 +20,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 
-CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "sgns_kernels.cu", "sgns_pipe.cu", "sgns_group.cu", "sgns_group_multi.cu", "sgns_pipe_multi.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu"]
+CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "sgns_kernels.cu", "sgns_pipe.cu", "sgns_group.cu", "sgns_group_multi.cu", "sgns_pipe_multi.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu", "serve_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 

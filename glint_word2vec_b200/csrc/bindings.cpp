@@ -9,6 +9,7 @@
 #include "launchers.h"
 #include "sgns_params.h"
 #include "nn_tc.h"
+#include "serve_params.h"
 
 namespace {
 
@@ -31,7 +32,7 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
                int64_t world, int64_t rank, int64_t tile_centers, int64_t slot_floats,
                std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs, int64_t xbuf_mc,
                c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing,
-               int64_t debug, int64_t variant) {
+               int64_t debug, int64_t variant, c10::optional<Tensor> exp_table) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
     CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
@@ -55,6 +56,12 @@ void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n
     p.K = (int)syn0.size(1);
     p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
     p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
+    p.exp_table = nullptr;
+    if (exp_table.has_value()) {
+        CHECK_CUDA(*exp_table); CHECK_CONTIG(*exp_table); CHECK_DT(*exp_table, torch::kFloat32);
+        TORCH_CHECK(exp_table->numel() == 1000, "exp_table must have 1000 entries");
+        p.exp_table = exp_table->data_ptr<float>();
+    }
     p.debug = (int)debug;
     p.world = (int)world; p.rank = (int)rank;
     p.tile_centers = (int)tile_centers; p.slot_floats = (int)slot_floats;
@@ -99,7 +106,8 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                      int64_t grid, int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs,
                      std::vector<int64_t> flag_ptrs, c10::optional<Tensor> warp_seq, c10::optional<Tensor> error_flag,
                      c10::optional<Tensor> timing, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs,
-                     Tensor desc, Tensor ticket, Tensor chain, int64_t epoch) {
+                     Tensor desc, Tensor ticket, Tensor chain, int64_t epoch, int64_t xbuf_mc, int64_t flags_mc,
+                     c10::optional<Tensor> exp_table) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
     CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
@@ -129,6 +137,12 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     p.K = (int)syn0.size(1);
     p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
     p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
+    p.exp_table = nullptr;
+    if (exp_table.has_value()) {
+        CHECK_CUDA(*exp_table); CHECK_CONTIG(*exp_table); CHECK_DT(*exp_table, torch::kFloat32);
+        TORCH_CHECK(exp_table->numel() == 1000, "exp_table must have 1000 entries");
+        p.exp_table = exp_table->data_ptr<float>();
+    }
     p.debug = (int)debug;
     p.world = (int)world; p.rank = (int)rank;
     gw2v::launch_pairgen(p.tokens, p.sent_id, p.n_tokens, (int)max_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi,
@@ -147,6 +161,8 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
         }
         p.error_flag = error_flag->data_ptr<int>();
         p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
+        p.xbuf_mc = reinterpret_cast<float*>(xbuf_mc);
+        p.flags_mc = reinterpret_cast<uint32_t*>(flags_mc);
         gw2v::launch_sgns_pairs_multi(p, desc.data_ptr<int>(), n_pairs.data_ptr<int>(), pd, (int)grid,
                                       reinterpret_cast<uint32_t*>(warp_seq->data_ptr<int>()), cur_stream());
     } else {
@@ -282,9 +298,186 @@ Tensor scores_tc(Tensor syn0, Tensor qs) {
 
 bool scores_tc_supported(int64_t K, int64_t Q) { return gw2v::scores_tc_supported((int)K, (int)Q); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Serving over column shards with the collective fused into the kernels (serve_fused.cu / nn_tc.cu).
+// One ServeCtx per engine: symmetric flag array pointers, the CTA arrival counter and the running sequence
+// number (every rank issues the same operations in the same order, so the numbers agree without traffic).
+struct ServeCtx {
+    int64_t world, rank;
+    std::vector<int64_t> flag_ptrs;
+    Tensor done, err;
+    int64_t seq = 0;
+
+    ServeCtx(int64_t world_, int64_t rank_, std::vector<int64_t> flag_ptrs_, Tensor done_, Tensor err_)
+        : world(world_), rank(rank_), flag_ptrs(std::move(flag_ptrs_)), done(done_), err(err_) {
+        TORCH_CHECK(world >= 1 && world <= gw2v::MAX_WORLD, "world size must be 1..", gw2v::MAX_WORLD);
+        TORCH_CHECK((int64_t)flag_ptrs.size() == world, "need one flag pointer per rank");
+        CHECK_CUDA(done); CHECK_CUDA(err); CHECK_DT(done, torch::kInt32); CHECK_DT(err, torch::kInt32);
+    }
+    gw2v::ServeSync next() {
+        ++seq;
+        gw2v::ServeSync s{};
+        for (int64_t r = 0; r < world; ++r) s.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+        s.done = reinterpret_cast<unsigned int*>(done.data_ptr<int>());
+        s.error_flag = err.data_ptr<int>();
+        s.world = (int)world; s.rank = (int)rank; s.seq = (uint32_t)seq;
+        return s;
+    }
+    void wait(const gw2v::ServeSync& s) {
+        gw2v::launch_serve_wait(s.flags[rank], (int)world, s.seq, s.error_flag, cur_stream());
+        check_launch("serve_wait");
+    }
+    void barrier() {
+        c10::cuda::CUDAGuard guard(done.device());
+        gw2v::ServeSync s = next();
+        gw2v::launch_serve_barrier(s, cur_stream());
+        check_launch("serve_barrier");
+    }
+};
+
+gw2v::PeerPtrs peer_ptrs(const ServeCtx& c, const std::vector<int64_t>& ptrs) {
+    TORCH_CHECK((int64_t)ptrs.size() == c.world, "need one buffer pointer per rank");
+    gw2v::PeerPtrs p{};
+    for (int64_t r = 0; r < c.world; ++r) p.p[r] = reinterpret_cast<float*>(ptrs[r]);
+    return p;
+}
+
+// pull(rows): every rank ends up with the full [R, world*K] rows in its own `out` buffer
+void serve_gather_push(ServeCtx& c, Tensor syn0, Tensor rows, std::vector<int64_t> out_ptrs, int64_t ldo) {
+    CHECK_CUDA(syn0); CHECK_CUDA(rows); CHECK_DT(rows, torch::kInt64); CHECK_CONTIG(syn0); CHECK_CONTIG(rows);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::ServeSync s = c.next();
+    gw2v::launch_gather_rows_push(syn0.data_ptr<float>(), reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()),
+                                  (int)rows.numel(), (int)syn0.size(1), peer_ptrs(c, out_ptrs), (int)ldo, s,
+                                  cur_stream());
+    check_launch("gather_rows_push");
+    c.wait(s);
+}
+
+void serve_segment_mean_push(ServeCtx& c, Tensor syn0, Tensor rows, Tensor offsets, std::vector<int64_t> out_ptrs,
+                             int64_t ldo) {
+    CHECK_CUDA(syn0); CHECK_CUDA(rows); CHECK_CUDA(offsets); CHECK_DT(rows, torch::kInt64);
+    CHECK_DT(offsets, torch::kInt64); CHECK_CONTIG(syn0); CHECK_CONTIG(rows); CHECK_CONTIG(offsets);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::ServeSync s = c.next();
+    gw2v::launch_segment_mean_push(syn0.data_ptr<float>(), reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()),
+                                   reinterpret_cast<const long long*>(offsets.data_ptr<int64_t>()),
+                                   (int)(offsets.numel() - 1), (int)syn0.size(1), peer_ptrs(c, out_ptrs), (int)ldo, s,
+                                   cur_stream());
+    check_launch("segment_mean_push");
+    c.wait(s);
+}
+
+// norms(), step 1: partial sums of squares -> the owner's slab [src][vown]
+void serve_sqnorm_push(ServeCtx& c, Tensor syn0, std::vector<int64_t> slab_ptrs, int64_t vown) {
+    CHECK_CUDA(syn0); CHECK_CONTIG(syn0);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::ServeSync s = c.next();
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    gw2v::launch_row_sqnorm_push(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), peer_ptrs(c, slab_ptrs),
+                                 vown, s, sms, cur_stream());
+    check_launch("row_sqnorm_push");
+    c.wait(s);
+}
+
+// owner sums the S partial slices (optionally sqrt) and all-gathers its slice into every rank's full vector
+void serve_reduce_finish_push(ServeCtx& c, Tensor slab_local, int64_t nsrc, int64_t vown, int64_t nvalid,
+                              bool take_sqrt, std::vector<int64_t> full_ptrs) {
+    CHECK_CUDA(slab_local); CHECK_DT(slab_local, torch::kFloat32);
+    c10::cuda::CUDAGuard guard(slab_local.device());
+    gw2v::ServeSync s = c.next();
+    gw2v::launch_reduce_finish_push(slab_local.data_ptr<float>(), (int)nsrc, vown, nvalid, take_sqrt ? 1 : 0,
+                                    peer_ptrs(c, full_ptrs), s, cur_stream());
+    check_launch("reduce_finish_push");
+    c.wait(s);
+}
+
+// partial score tiles -> the owner's slab [src][Q][vown]  (tcgen05 GEMM epilogue or the CUDA-core kernel)
+void serve_scores_push(ServeCtx& c, Tensor syn0, Tensor qs, std::vector<int64_t> slab_ptrs, int64_t vown,
+                       bool use_tc) {
+    CHECK_CUDA(syn0); CHECK_CUDA(qs); CHECK_CONTIG(syn0); CHECK_CONTIG(qs);
+    TORCH_CHECK(qs.size(1) == syn0.size(1), "query slice width != shard columns");
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::ServeSync s = c.next();
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    if (use_tc) {
+        TORCH_CHECK(gw2v::scores_tc_supported((int)syn0.size(1), (int)qs.size(0)), "scores_tc: unsupported shape");
+        int qp = gw2v::scores_tc_padded_queries((int)qs.size(0));
+        auto qpad = torch::zeros({qp, qs.size(1)}, qs.options());
+        qpad.narrow(0, 0, qs.size(0)).copy_(qs);
+        int rc = gw2v::launch_scores_tc_push(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1),
+                                             qpad.data_ptr<float>(), (int)qs.size(0), peer_ptrs(c, slab_ptrs), vown, s,
+                                             sms, cur_stream());
+        TORCH_CHECK(rc == 0, "scores_tc_push failed (rc=", rc, ")");
+    } else {
+        TORCH_CHECK(qs.size(0) * qs.size(1) * 4 <= 200 * 1024, "query batch too large for the CUDA-core path");
+        gw2v::launch_scores_rows_push(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), qs.data_ptr<float>(),
+                                      (int)qs.size(0), peer_ptrs(c, slab_ptrs), vown, s, sms, cur_stream());
+    }
+    check_launch("scores_push");
+    c.wait(s);
+}
+
+// owner: sum the S partial score slices, / norm, top-k of the owned rows; winners pushed to every rank [q][src][k]
+void serve_topk_owned_push(ServeCtx& c, Tensor slab_local, int64_t nsrc, int64_t Q, int64_t vown, int64_t nvalid,
+                           Tensor norms_owned, int64_t row_base, int64_t k, std::vector<int64_t> candv_ptrs,
+                           std::vector<int64_t> candi_ptrs) {
+    CHECK_CUDA(slab_local); CHECK_CUDA(norms_owned);
+    c10::cuda::CUDAGuard guard(slab_local.device());
+    gw2v::ServeSync s = c.next();
+    int nchunks = gw2v::topk_owned_num_chunks(nvalid);
+    auto cand_v = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, slab_local.options());
+    auto cand_i = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, slab_local.options().dtype(torch::kInt64));
+    gw2v::PeerIdx pi{};
+    TORCH_CHECK((int64_t)candi_ptrs.size() == c.world, "need one candidate-index pointer per rank");
+    for (int64_t r = 0; r < c.world; ++r) pi.p[r] = reinterpret_cast<long long*>(candi_ptrs[r]);
+    gw2v::launch_topk_owned_push(slab_local.data_ptr<float>(), (int)nsrc, (int)Q, vown, nvalid,
+                                 norms_owned.data_ptr<float>(), row_base, (int)k, cand_v.data_ptr<float>(),
+                                 reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()), peer_ptrs(c, candv_ptrs), pi,
+                                 s, cur_stream());
+    check_launch("topk_owned_push");
+    c.wait(s);
+}
+
+// final merge of the world*k candidates per query (destroys cand_v)
+std::vector<Tensor> serve_topk_final(Tensor cand_v, Tensor cand_i, int64_t k) {
+    CHECK_CUDA(cand_v); CHECK_CUDA(cand_i); CHECK_CONTIG(cand_v); CHECK_CONTIG(cand_i);
+    c10::cuda::CUDAGuard guard(cand_v.device());
+    int64_t Q = cand_v.size(0), ncand = cand_v.size(1);
+    auto out_v = torch::empty({Q, k}, cand_v.options());
+    auto out_i = torch::empty({Q, k}, cand_i.options());
+    gw2v::launch_topk_merge(cand_v.data_ptr<float>(), reinterpret_cast<const long long*>(cand_i.data_ptr<int64_t>()),
+                            (int)ncand, (int)Q, (int)k, out_v.data_ptr<float>(),
+                            reinterpret_cast<long long*>(out_i.data_ptr<int64_t>()), cur_stream());
+    check_launch("topk_merge");
+    return {out_i, out_v};
+}
+
+// tiny all-gather: every rank's n floats -> [world, n] on every rank
+void serve_push_block(ServeCtx& c, Tensor src, std::vector<int64_t> dst_ptrs) {
+    CHECK_CUDA(src); CHECK_CONTIG(src); CHECK_DT(src, torch::kFloat32);
+    c10::cuda::CUDAGuard guard(src.device());
+    gw2v::ServeSync s = c.next();
+    gw2v::launch_push_block(src.data_ptr<float>(), src.numel(), peer_ptrs(c, dst_ptrs), s, cur_stream());
+    check_launch("push_block");
+    c.wait(s);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    py::class_<ServeCtx>(m, "ServeCtx")
+        .def(py::init<int64_t, int64_t, std::vector<int64_t>, Tensor, Tensor>())
+        .def("barrier", &ServeCtx::barrier)
+        .def_readonly("seq", &ServeCtx::seq);
+    m.def("serve_gather_push", &serve_gather_push);
+    m.def("serve_segment_mean_push", &serve_segment_mean_push);
+    m.def("serve_sqnorm_push", &serve_sqnorm_push);
+    m.def("serve_reduce_finish_push", &serve_reduce_finish_push);
+    m.def("serve_scores_push", &serve_scores_push);
+    m.def("serve_topk_owned_push", &serve_topk_owned_push);
+    m.def("serve_topk_final", &serve_topk_final);
+    m.def("serve_push_block", &serve_push_block);
     m.def("sgns_step", &sgns_step);
     m.def("sgns_step_pairs", &sgns_step_pairs);
     m.def("sgns_pairs_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_pairs_supported((int)K, (int)w, (int)n); });

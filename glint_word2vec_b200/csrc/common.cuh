@@ -70,9 +70,18 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---------------------------------------------------------------- sigmoid / coefficient
 constexpr float MAX_EXP = 6.0f;
 
-// g = (label - sigmoid(f)) * alpha with the reference's hard clip at +-6 (MLLIB:292-302)
-__device__ __forceinline__ float sgns_coeff(float f, float label, float alpha, float max_grad) {
-    float sig = 1.0f / (1.0f + __expf(-f));
+// g = (label - sigmoid(f)) * alpha with the reference's hard clip at +-6 (MLLIB:292-302).
+// table != null: the reference's 1000-entry lookup with its index scale 83.0 (integer 1000/6, MLLIB:296).
+__device__ __forceinline__ float sgns_coeff(float f, float label, float alpha, float max_grad,
+                                            const float* __restrict__ table = nullptr) {
+    float sig;
+    if (table != nullptr) {
+        int ind = (int)((f + MAX_EXP) * 83.0f);
+        ind = min(max(ind, 0), 999);
+        sig = __ldg(table + ind);
+    } else {
+        sig = 1.0f / (1.0f + __expf(-f));
+    }
     float g = label - sig;
     if (f > MAX_EXP) g = label - 1.0f;
     if (f < -MAX_EXP) g = label;

@@ -220,6 +220,12 @@ topk_merge_kernel(float* __restrict__ cand_v, const long long* __restrict__ cand
     }
 }
 
+void launch_topk_merge(float* cand_v, const long long* cand_i, int ncand, int Q, int k, float* out_v,
+                       long long* out_i, cudaStream_t s) {
+    if (Q <= 0) return;
+    topk_merge_kernel<<<Q, TK_THREADS, 0, s>>>(cand_v, cand_i, ncand, k, out_v, out_i);
+}
+
 int topk_num_chunks(long long V) { return (int)((V + TK_CHUNK - 1) / TK_CHUNK); }
 
 void launch_cosine_topk(const float* scores, const float* norms, long long V, int Q, int k, float* cand_v,

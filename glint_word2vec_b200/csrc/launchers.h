@@ -36,5 +36,7 @@ void launch_scores_rows(const float* syn0, long long V, int K, const float* qs, 
 int topk_num_chunks(long long V);
 void launch_cosine_topk(const float* scores, const float* norms, long long V, int Q, int k, float* cand_v,
                         long long* cand_i, float* out_v, long long* out_i, cudaStream_t s);
+void launch_topk_merge(float* cand_v, const long long* cand_i, int ncand, int Q, int k, float* out_v,
+                       long long* out_i, cudaStream_t s);
 
 }  // namespace gw2v

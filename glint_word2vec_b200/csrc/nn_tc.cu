@@ -15,6 +15,7 @@
 // A = syn0 rows (M, K-major), B = queries (N, K-major): both operands are exactly their natural
 // row-major layout, no transposes anywhere.
 #include "nn_tc.h"
+#include "serve_common.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -123,7 +124,8 @@ __host__ __device__ inline SmemLayout smem_layout(int BN) {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scores_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ out, long long V, int Q, int K, int num_tiles) {
+                 const PeerPtrs outp, const long long vown, const ServeSync sync, long long V, int Q, int K,
+                 int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     const SmemLayout L = smem_layout(BN);
     const int STAGES = L.stages;
@@ -213,6 +215,11 @@ scores_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(tfull + acc, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row = (long long)tile * BM + quad * 32 + lane;
+            // reduce-scatter epilogue: row v belongs to rank v / vown; the partial score goes straight into that
+            // rank's slab [src rank][Q][vown] over NVLink (single shard: owner 0, vown >= V, plain [Q, V] output)
+            const int owner = (int)(row / vown);
+            float* __restrict__ out = outp.p[row < V ? owner : 0] + (size_t)sync.rank * (size_t)Q * (size_t)vown +
+                                      (size_t)(row - (long long)owner * vown);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -222,7 +229,7 @@ scores_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (row < V) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < Q) out[(size_t)(c0 + j) * (size_t)V + (size_t)row] = __uint_as_float(r[j]);
+                        if (c0 + j < Q) out[(size_t)(c0 + j) * (size_t)vown] = __uint_as_float(r[j]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,6 +243,7 @@ scores_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
+    if (sync.world > 1) serve_cta_done(sync);       // last CTA publishes the sequence number to every rank
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -265,7 +273,8 @@ bool make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, 
 }
 
 template <int BN>
-int launch_bn(const float* syn0, long long V, int K, const float* qpad, int Q, float* out, int sms, cudaStream_t s) {
+int launch_bn(const float* syn0, long long V, int K, const float* qpad, int Q, const PeerPtrs& outp, long long vown,
+              const ServeSync& sync, int sms, cudaStream_t s) {
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, syn0, (uint64_t)V, (uint64_t)K, BM)) return 2;
     if (!make_map(&tmB, qpad, (uint64_t)BN, (uint64_t)K, BN)) return 2;
@@ -273,7 +282,7 @@ int launch_bn(const float* syn0, long long V, int K, const float* qpad, int Q, f
     SmemLayout L = smem_layout(BN);
     cudaFuncSetAttribute(scores_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     int grid = num_tiles < sms ? num_tiles : sms;
-    scores_tc_kernel<BN><<<grid, NUM_THREADS, L.total, s>>>(tmA, tmB, out, V, Q, K, num_tiles);
+    scores_tc_kernel<BN><<<grid, NUM_THREADS, L.total, s>>>(tmA, tmB, outp, vown, sync, V, Q, K, num_tiles);
     return 0;
 }
 
@@ -290,16 +299,26 @@ int scores_tc_padded_queries(int Q) {
 bool scores_tc_supported(int K, int Q) { return K >= BK && K % BK == 0 && Q >= 1 && Q <= 256; }
 
 // qpad: [scores_tc_padded_queries(Q), K] row-major, zero padded
-int launch_scores_tc(const float* syn0, long long V, int K, const float* qpad, int Q, float* out, int sms,
-                     cudaStream_t stream) {
+int launch_scores_tc_push(const float* syn0, long long V, int K, const float* qpad, int Q, const PeerPtrs& slab,
+                          long long vown, const ServeSync& sync, int sms, cudaStream_t stream) {
     if (!scores_tc_supported(K, Q) || V <= 0) return 1;
     switch (scores_tc_padded_queries(Q)) {
-        case 16: return launch_bn<16>(syn0, V, K, qpad, Q, out, sms, stream);
-        case 32: return launch_bn<32>(syn0, V, K, qpad, Q, out, sms, stream);
-        case 64: return launch_bn<64>(syn0, V, K, qpad, Q, out, sms, stream);
-        case 128: return launch_bn<128>(syn0, V, K, qpad, Q, out, sms, stream);
-        default: return launch_bn<256>(syn0, V, K, qpad, Q, out, sms, stream);
+        case 16: return launch_bn<16>(syn0, V, K, qpad, Q, slab, vown, sync, sms, stream);
+        case 32: return launch_bn<32>(syn0, V, K, qpad, Q, slab, vown, sync, sms, stream);
+        case 64: return launch_bn<64>(syn0, V, K, qpad, Q, slab, vown, sync, sms, stream);
+        case 128: return launch_bn<128>(syn0, V, K, qpad, Q, slab, vown, sync, sms, stream);
+        default: return launch_bn<256>(syn0, V, K, qpad, Q, slab, vown, sync, sms, stream);
     }
+}
+
+// single shard: plain [Q, V] output (owner 0 for every row, no signal)
+int launch_scores_tc(const float* syn0, long long V, int K, const float* qpad, int Q, float* out, int sms,
+                     cudaStream_t stream) {
+    PeerPtrs o{};
+    o.p[0] = out;
+    ServeSync sync{};
+    sync.world = 1; sync.rank = 0;
+    return launch_scores_tc_push(syn0, V, K, qpad, Q, o, V, sync, sms, stream);
 }
 
 }  // namespace gw2v

@@ -106,7 +106,7 @@ sgns_fused_group_kernel(const SgnsParams p) {
             const int myrow = rb + row_of_lane<G>(lane);
             const float mylabel = (myrow == 0) ? 1.f : 0.f;
             const bool myact = gvalid && (myrow <= n) && (myrow == 0 || e[4 + myrow - 1] != ctok);
-            const float gmine = myact ? sgns_coeff(ftot, mylabel, p.alpha, p.max_grad) : 0.f;
+            const float gmine = myact ? sgns_coeff(ftot, mylabel, p.alpha, p.max_grad, p.exp_table) : 0.f;
             if (p.compute_loss && myact && lg == lane_of_row<G>(row_of_lane<G>(lane))) {
                 loss += softplus_clipped(mylabel > 0.5f ? -ftot : ftot);
                 maxdot = fmaxf(maxdot, fabsf(ftot));

@@ -211,7 +211,7 @@ sgns_fused_group_multi_kernel(const SgnsParams p, uint32_t* warp_seq) {
             const bool myact = gvalid && (myrow <= n) && (myrow == 0 || e[4 + myrow - 1] != ctok);
             const float fm = fdot[(pidx % GM_RF) * GM_FP + myrow];
             const float mylabel = (myrow == 0) ? 1.f : 0.f;
-            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad) : 0.f;
+            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad, p.exp_table) : 0.f;
             if (p.compute_loss && myact && lg == lane_of_row<G>(myrow)) {
                 loss += softplus_clipped(mylabel > 0.5f ? -fm : fm);
                 maxdot = fmaxf(maxdot, fabsf(fm));

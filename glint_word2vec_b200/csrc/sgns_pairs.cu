@@ -29,7 +29,7 @@ namespace gw2v {
 constexpr int PK_THREADS = 256;
 constexpr int PK_FP = 8;              // floats per pair in exchange slots (1 + n <= 8)
 constexpr int PK_BATCH = 4;           // pairs per batch: slot = 32 floats = 128 B
-constexpr int PK_LAG = 16;            // pairs between pass A and pass B
+constexpr int PK_LAG = 16;            // max pairs between pass A and pass B (template parameter LAG: 4 or 16)
 constexpr int PK_NSLOT = 14;          // >= 2 * (batches in flight + 1)
 
 template <int G> __device__ __forceinline__ int pk_row_of_lane(int lane) {
@@ -150,7 +150,7 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
         for (int r = 0; r < 8; ++r) actmask |= ract[r] ? (1u << r) : 0u;
         const bool myact = (actmask >> myrow) & 1u;
         const float mylabel = (myrow == 0) ? 1.f : 0.f;
-        const float gmine = myact ? sgns_coeff(ftot, mylabel, p.alpha, p.max_grad) : 0.f;
+        const float gmine = myact ? sgns_coeff(ftot, mylabel, p.alpha, p.max_grad, p.exp_table) : 0.f;
         if (p.compute_loss && myact && owner) {
             loss += softplus_clipped(mylabel > 0.5f ? -ftot : ftot);
             maxdot = fmaxf(maxdot, fabsf(ftot));
@@ -196,13 +196,18 @@ struct PkWarpSmem {
     float xsum[8 * 32];                  // per-source copy of one batch for the ordered reduction
 };
 
-template <int G, int CHUNKS, int MINB>
+// LAG = pairs between pass A and pass B of a warp.  The rows touched in between must still be in L2 when
+// pass B re-gathers them: in-flight footprint = LAG x warps x (2+n) rows.  LAG 16 at K=256 is 265 MB (> the
+// 126 MB L2, pass B then re-reads DRAM: measured 1.21 ms vs 0.62 ms for the exchange-free kernel); one batch
+// (LAG 4, ~35 us of work per warp) already covers the ~2-3 us NVLink round trip many times over.
+template <int G, int CHUNKS, int MINB, int LAG>
 __global__ void __launch_bounds__(PK_THREADS, MINB)
 sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr,
                         const int pd, uint32_t* warp_seq) {
     constexpr int P = 32 / G;
     constexpr int BS = PK_BATCH / P;           // steps per batch
-    constexpr int LAGS = PK_LAG / P;           // lag in steps
+    static_assert(LAG % PK_BATCH == 0 && LAG <= PK_LAG, "lag must be whole batches");
+    constexpr int LAGS = LAG / P;              // lag in steps
     constexpr int RFS = 2 * LAGS;              // dot ring in steps (multiple of BS)
     __shared__ __align__(16) PkWarpSmem wsm[PK_THREADS / 32];
     const int lane = threadIdx.x & 31;
@@ -277,7 +282,21 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 const int b = k / BS;
                 const uint32_t bseq = seq0 + (uint32_t)b;
                 const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
-                if (lane < S && lane != rank) {
+                if (p.xbuf_mc != nullptr) {
+                    // NVLS: ONE multicast store per 16 bytes lands in every rank's slot (switch-replicated),
+                    // then a multicast release-store publishes the sequence number everywhere
+                    const float4* src = reinterpret_cast<const float4*>(fdot + (size_t)((b * BS) % RFS) * P * PK_FP);
+                    float* dstmc = p.xbuf_mc + warp_x_base + ((size_t)slot * S + rank) * slot_stride;
+                    if (lane < 8) {
+                        const float4 x = src[lane];
+                        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"l"(dstmc + 4 * lane), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("multimem.st.release.sys.global.b32 [%0], %1;"
+                                     ::"l"(p.flags_mc + (size_t)gwarp * S + rank), "r"(bseq + 1u) : "memory");
+                } else if (lane < S && lane != rank) {
                     float4* dst = reinterpret_cast<float4*>(p.xbuf[lane] + warp_x_base +
                                                             ((size_t)slot * S + rank) * slot_stride);
                     const float4* src = reinterpret_cast<const float4*>(fdot + (size_t)((b * BS) % RFS) * P * PK_FP);
@@ -359,7 +378,7 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             for (int r = 0; r < 8; ++r) actmask |= ract[r] ? (1u << r) : 0u;
             const bool myact = (actmask >> myrow) & 1u;
             const float mylabel = (myrow == 0) ? 1.f : 0.f;
-            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad) : 0.f;
+            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad, p.exp_table) : 0.f;
             if (p.compute_loss && myact && owner) {
                 loss += softplus_clipped(mylabel > 0.5f ? -fm : fm);
                 maxdot = fmaxf(maxdot, fabsf(fm));
@@ -422,6 +441,12 @@ static int pk_occ() {
     if (occ < 0) { const char* e = getenv("GW2V_PAIRS_OCC"); occ = e ? atoi(e) : 3; }
     return occ;
 }
+// pairs between pass A and pass B of the column-shard kernel (4 = one batch, 16 = four batches)
+static int pk_lag() {
+    static int lag = -1;
+    if (lag < 0) { const char* e = getenv("GW2V_PAIRS_LAG"); lag = (e && atoi(e) >= 16) ? 16 : 4; }
+    return lag;
+}
 
 #define GW2V_PK_DISPATCH(K, CALL)                                            \
     do {                                                                     \
@@ -442,7 +467,13 @@ int sgns_pairs_grid(int K, int device, bool multi) {
     int sms = 148, occ = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (multi) {
-#define CALL(GG, C, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB>, PK_THREADS, 0)
+#define CALL(GG, C, MB)                                                                                              \
+    do {                                                                                                             \
+        if (pk_lag() >= 16)                                                                                          \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB, 16>, PK_THREADS, 0); \
+        else                                                                                                         \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB, 4>, PK_THREADS, 0);  \
+    } while (0)
         GW2V_PK_DISPATCH(K, CALL);
 #undef CALL
     } else {
@@ -468,7 +499,13 @@ void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs,
 
 void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
                              uint32_t* warp_seq, cudaStream_t stream) {
-#define CALL(GG, C, MB) sgns_pairs_multi_kernel<GG, C, MB><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq)
+#define CALL(GG, C, MB)                                                                                        \
+    do {                                                                                                       \
+        if (pk_lag() >= 16)                                                                                    \
+            sgns_pairs_multi_kernel<GG, C, MB, 16><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq); \
+        else                                                                                                   \
+            sgns_pairs_multi_kernel<GG, C, MB, 4><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq);  \
+    } while (0)
     GW2V_PK_DISPATCH(p.K, CALL);
 #undef CALL
 }

@@ -22,6 +22,7 @@ struct SgnsParams {
     int K;                       // row stride in floats (multiple of 4)
     int window, negatives, window_mode;   // window_mode 0 = reference (Q2), 1 = word2vec.c
     float alpha, max_grad;
+    const float* exp_table;      // 1000-entry sigma table on [-6,6] (MLLIB:281-302 parity mode) or null = exact
     int compute_loss;
     int debug;                   // profiling only: bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads
     // ---- cross-shard exchange (world > 1)
@@ -31,6 +32,7 @@ struct SgnsParams {
     float* xbuf[MAX_WORLD];      // peer-mapped exchange buffers, xbuf[r] lives on rank r
     uint32_t* flags[MAX_WORLD];  // peer-mapped flag arrays [grid * world]
     float* xbuf_mc;              // multicast alias of xbuf (NVLS), or null
+    uint32_t* flags_mc;          // multicast alias of the flag arrays, or null
     uint32_t* cta_seq;           // [grid] running tile sequence number per CTA (local)
     int* error_flag;             // set by the spin watchdog
     unsigned long long* timing;  // optional [grid*2]: accumulated wait ns, tiles (exposed all-reduce time)

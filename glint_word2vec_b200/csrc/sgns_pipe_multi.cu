@@ -276,7 +276,7 @@ sgns_fused_pipe_multi_kernel(const SgnsParams p, const MultiPipeArgs a) {
             const bool myact = gvalid && (myrow <= n) && (myrow == 0 || e[4 + myrow - 1] != ctok);
             const float fm = fdot[(pidx % M_RF) * M_FP + myrow];
             const float mylabel = (myrow == 0) ? 1.f : 0.f;
-            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad) : 0.f;
+            const float gmine = myact ? sgns_coeff(fm, mylabel, p.alpha, p.max_grad, p.exp_table) : 0.f;
             if (p.compute_loss && myact && lg == lane_of_row<G>(myrow)) {
                 loss += softplus_clipped(mylabel > 0.5f ? -fm : fm);
                 maxdot = fmaxf(maxdot, fabsf(fm));

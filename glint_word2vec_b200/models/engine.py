@@ -220,6 +220,9 @@ class ShardEngine:
     def pull(self, rows) -> torch.Tensor:
         """Full [R, d] input vectors for ``rows`` (collective)."""
         rows = torch.as_tensor(rows, dtype=torch.int64)
+        if self.is_cuda and self._cuda.serve_fused:
+            # the column all-gather happens inside the gather kernel (peer stores over NVLink)
+            return self._cuda.serve().pull(self._cuda._rows_dev(rows))[:, :self.cfg.vector_size]
         if self.is_cuda:
             part = self._cuda.gather_rows(rows)
         else:
@@ -232,6 +235,9 @@ class ShardEngine:
         rows_flat = torch.as_tensor(rows_flat, dtype=torch.int64)
         offsets = torch.as_tensor(offsets, dtype=torch.int64)
         ns = offsets.shape[0] - 1
+        if self.is_cuda and self._cuda.serve_fused:
+            full = self._cuda.serve().pull_average(self._cuda._rows_dev(rows_flat), self._cuda._rows_dev(offsets))
+            return full[:, :self.cfg.vector_size]
         if self.is_cuda:
             part = self._cuda.segment_mean_rows(rows_flat, offsets)
         else:
@@ -246,6 +252,9 @@ class ShardEngine:
 
     def norms(self) -> torch.Tensor:
         """Euclidean norm of every input vector, [V] (cached; collective)."""
+        if self._norms is None and self.is_cuda and self._cuda.serve_fused:
+            # reduce-scatter + sqrt + all-gather inside the kernels (ops/serving.py)
+            self._norms = self._cuda.serve().norms()
         if self._norms is None:
             if self.is_cuda:
                 sq = self._cuda.row_sqnorm()
@@ -269,6 +278,9 @@ class ShardEngine:
 
     def _scores(self, q: torch.Tensor) -> torch.Tensor:
         qs = self._query_slice(q)
+        if self.is_cuda and self._cuda.serve_fused:
+            sx = self._cuda.serve()
+            return torch.stack([sx.multiply(qs[i:i + 1]) for i in range(qs.shape[0])], 0)
         if self.is_cuda:
             part = self._cuda.scores(qs)              # [Q, V]
         else:

@@ -57,7 +57,16 @@ class CudaShardOps:
         self.launches = 0                    # kernel launches issued by this object (bench bookkeeping)
         self._count_val = -1
         self.debug = int(os.environ.get("GW2V_DEBUG", "0"))      # profiling-only kernel switches
+        # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
+        self.exp_table = None
+        if engine.cfg.sigmoid_mode == "table":
+            from ..models.sgns import _exp_table
+            self.exp_table = _exp_table().to(self.dev).contiguous()
         self._props = torch.cuda.get_device_properties(self.dev)
+        # world > 1: serving collectives are fused into the kernels (ops/serving.py); GW2V_SERVE_FUSED=0 falls
+        # back to kernel + NCCL collective (kept for A/B measurements)
+        self.serve_fused = self.world > 1 and os.environ.get("GW2V_SERVE_FUSED", "1") != "0"
+        self._serve = None
 
     # ------------------------------------------------------------------ setup
     def init_weights(self, seed: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -75,6 +84,7 @@ class CudaShardOps:
 
     def release(self):
         self._xchg = None
+        self._serve = None
         self.alias_dev = self.keep_dev = None
         self._cap = 0
 
@@ -154,6 +164,9 @@ class CudaShardOps:
             "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats, "variant": variant,
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
             "mc": buf.multicast_ptr,
+            # NVLS multicast push (multimem.st) is opt-in: GW2V_NVLS=1 and a multicast mapping granted by the driver
+            "mc_x": buf.multicast_ptr if (buf.multicast_ptr and os.environ.get("GW2V_NVLS", "0") == "1") else 0,
+            "mc_f": (buf.multicast_ptr + xbytes) if (buf.multicast_ptr and os.environ.get("GW2V_NVLS", "0") == "1") else 0,
             "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
             "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
         }
@@ -214,7 +227,7 @@ class CudaShardOps:
                                float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank,
                                x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
                                self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_ticket,
-                               self.pg_chain, self._pg_epoch)
+                               self.pg_chain, self._pg_epoch, x["mc_x"], x["mc_f"], self.exp_table)
             self.launches += 3            # + the training kernel counted below
         elif self.world > 1:
             x = self._xchg
@@ -222,7 +235,7 @@ class CudaShardOps:
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank, x["tb"],
                          x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing,
-                         self.debug, x["variant"])
+                         self.debug, x["variant"], self.exp_table)
         else:
             if not hasattr(self, "_grid1"):
                 self._variant, self._grid1 = self._pick_single_kernel()
@@ -232,15 +245,35 @@ class CudaShardOps:
                                    int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                    float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
                                    None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
-                                   self.pg_ticket, self.pg_chain, self._pg_epoch)
+                                   self.pg_ticket, self.pg_chain, self._pg_epoch, 0, 0, self.exp_table)
                 self.launches += 4            # pair_count, pair_tile_scan, pair_fill, sgns_pairs
                 return stats
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
                          int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                          float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
-                         None, None, None, self.debug, self._variant)
+                         None, None, None, self.debug, self._variant, self.exp_table)
         self.launches += 1
         return stats
+
+    def _top_k_fused(self, qs: torch.Tensor, norms: torch.Tensor, k: int, tc: bool):
+        """world > 1: score GEMM with a reduce-scatter epilogue, per-owner top-k, candidate exchange -
+        all inside the kernels.  With tf32 screening the k+16 survivors are re-scored in exact fp32."""
+        sx = self.serve()
+        v = self.cfg.vocab_size
+        nq = qs.shape[0]
+        if not tc:
+            return sx.top_k(qs, k, False)
+        kk = min(v, k + 16)
+        idx, _ = sx.top_k(qs, kk, True)
+        safe = idx.clamp(min=0)
+        rows = _C.gather_rows(self.e.syn0, safe.reshape(-1).contiguous()).view(nq, kk, self.K)
+        self.launches += 1
+        dots = sx.allgather_sum((rows * qs[:, None, :]).sum(-1))          # exact fp32, fixed rank order
+        nr = norms[safe]
+        cos = torch.where((nr > 0) & (idx >= 0), dots / nr.clamp(min=1e-30), torch.zeros_like(dots))
+        cos = torch.where(idx >= 0, cos, torch.full_like(cos, -3.0e38))
+        sim, order = torch.sort(cos, dim=1, descending=True)
+        return torch.gather(idx, 1, order)[:, :k].contiguous(), sim[:, :k].contiguous()
 
     def _pick_single_kernel(self):
         """single-shard kernel variant: 2 = lane-group register path, 1 = TMA pipeline, 0 = v1."""
@@ -263,6 +296,13 @@ class CudaShardOps:
         return 0, int(_C.sgns_single_grid(self.K, dev_index))
 
     # ------------------------------------------------------------------ inference
+    def serve(self):
+        """Lazily allocated symmetric serving workspace (collective on first use)."""
+        if self._serve is None:
+            from .serving import ServeExchange
+            self._serve = ServeExchange(self)
+        return self._serve
+
     def _rows_dev(self, rows: torch.Tensor) -> torch.Tensor:
         return rows.to(self.dev, torch.int64).contiguous()
 
@@ -304,6 +344,8 @@ class CudaShardOps:
         nq = qs.shape[0]
         v = self.cfg.vocab_size
         tc = self._use_tc(nq)
+        if self.serve_fused:
+            return self._top_k_fused(qs.contiguous(), norms, int(k), tc)
         part = self.scores(qs, allow_tc=tc)
         full = self.e.comm.all_reduce_sum(part)
         self.launches += 1

@@ -57,6 +57,10 @@ def _worker(rank, world, port, d, out_dir):
         got0 = eng.pull(torch.arange(v)).cpu()
         nrm = eng.norms().cpu()
         idx, sim = eng.top_k(got0[:4], 5)
+        # serving ops with the collective fused into the kernels (ops/serving.py)
+        avg = eng.pull_average(torch.tensor([1, 2, 3, 7, 9]), torch.tensor([0, 3, 3, 5])).cpu()
+        mul = eng.multiply(got0[5]).cpu()
+        idx16, sim16 = eng.top_k(got0[100:116], 7)          # Q = 16: tcgen05 screening + exact re-rank when K % 32 == 0
         if rank == 0:
             # oracle: dense single-process mini-batch semantics, one mini-batch per step
             ref0, _ = sgns.init_embeddings(v, d, 11)
@@ -68,17 +72,24 @@ def _worker(rank, world, port, d, out_dir):
                 st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, s * t, 0, 0.05)
                 pairs.append(st.pairs)
             torch.save({"got0": got0, "ref0": ref0, "start0": start0, "pairs": pairs,
-                        "stats": torch.stack(stats), "nrm": nrm, "idx": idx, "sim": sim},
+                        "stats": torch.stack(stats), "nrm": nrm, "idx": idx, "sim": sim,
+                        "avg": avg, "mul": mul, "idx16": idx16, "sim16": sim16},
                        os.path.join(out_dir, "result.pt"))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,d", [(2, 128), (2, 100), (4, 256), (8, 512)])
-def test_fused_multi_matches_oracle(world, d, tmp_path):
+@pytest.mark.parametrize("world,d,nvls,serve_fused", [(2, 128, 0, 1), (2, 100, 0, 1), (2, 128, 1, 0), (4, 256, 0, 1),
+                                                      (8, 512, 0, 1), (8, 512, 1, 1)])
+def test_fused_multi_matches_oracle(world, d, nvls, serve_fused, tmp_path, monkeypatch):
+    """nvls=1: the batch push uses multimem.st on the NVLS multicast mapping when the driver grants one
+    (falls back to per-peer stores otherwise).  serve_fused=0: serving ops as kernel + NCCL collective
+    instead of the in-kernel peer pushes."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("GW2V_NVLS", str(nvls))
+    monkeypatch.setenv("GW2V_SERVE_FUSED", str(serve_fused))
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), d, str(tmp_path)), nprocs=world, join=True)
     r = torch.load(os.path.join(tmp_path, "result.pt"))
@@ -91,3 +102,13 @@ def test_fused_multi_matches_oracle(world, d, tmp_path):
     # each of the first rows is its own nearest neighbour with cosine 1
     assert r["idx"][:, 0].tolist() == [0, 1, 2, 3]
     assert torch.allclose(r["sim"][:, 0], torch.ones(4), atol=1e-4)
+    g = r["got0"]
+    want_avg = torch.stack([g[[1, 2, 3]].mean(0), torch.zeros(d), g[[7, 9]].mean(0)])
+    assert torch.allclose(r["avg"], want_avg, atol=1e-6)
+    assert torch.allclose(r["mul"], g @ g[5], rtol=1e-4, atol=1e-5)
+    gn = g / g.norm(dim=1, keepdim=True).clamp(min=1e-30)
+    cos = gn[100:116] @ gn.t()
+    want_sim, want_idx = torch.topk(cos, 7, dim=1)
+    assert torch.allclose(r["sim16"], want_sim, atol=2e-5)
+    assert (r["idx16"] == want_idx).float().mean() > 0.98          # ties / last-place swaps only
+    assert r["idx16"][:, 0].tolist() == list(range(100, 116))

@@ -133,6 +133,39 @@ def test_sgns_step_single_matches_oracle(d, window, n, wmode, variant, monkeypat
     assert float(eng.syn0[:, d:].abs().sum()) == 0.0 or eng.shard.cols == d
 
 
+@pytest.mark.parametrize("variant", ["pairs", "group"])
+def test_sgns_step_sigmoid_table_mode(variant, monkeypatch):
+    """sigmoid_mode="table": the kernels look sigma up in the reference's 1000-entry table (MLLIB:281-302,
+    index scale 83.0) - diffed against the oracle in the same mode, with dots spread over [-6, 6] and beyond."""
+    dev = _dev()
+    monkeypatch.setenv("GW2V_SINGLE_KERNEL", variant)
+    v, d = 50000, 64
+    cfg = SGNSConfig(v, d, 5, 5, seed=7, sigmoid_mode="table")
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng.init_weights()
+    eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
+    g = torch.Generator().manual_seed(0)
+    syn1 = torch.randn(v, d, generator=g) * (2.0 / d ** 0.5)
+    syn0 = torch.randn(v, d, generator=g) * (2.0 / d ** 0.5)
+    eng.syn0, eng.syn1 = syn0.to(dev), syn1.to(dev)
+    t = 2000
+    tokens = np.random.default_rng(1).choice(v, size=t, replace=False).astype(np.int32)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0.clone(), syn1.clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 0, 0, 0.0005)
+    ex0, ex1 = syn0.clone(), syn1.clone()
+    import dataclasses
+    sgns.sgns_minibatch_reference(ex0, ex1, dataclasses.replace(cfg, sigmoid_mode="exact"), eng.alias, tokens, sid,
+                                  0, 0, 0.0005)
+    stats = eng.train_step(tokens, sid, 0, 0, 0.0005).cpu()
+    assert int(stats[0]) == st.pairs
+    d0, r0, e0 = eng.syn0.cpu() - syn0, ref0 - syn0, ex0 - syn0
+    err_table = float((d0 - r0).norm() / r0.norm())
+    assert err_table < 2e-2
+    # the two modes are distinguishable on this input
+    assert float((e0 - r0).norm() / r0.norm()) > 1e-4
+
+
 def test_sgns_step_hot_rows_hogwild_close():
     """Dense collisions (tiny vocabulary): updates race by design; the result
     must still be close to the summed mini-batch oracle and finite."""
