@@ -9,7 +9,7 @@ re-launches itself under ``torch.distributed.run`` on 127.0.0.1.
 
 One JSON line on rank 0.  ``value`` is the whole-job device-timed throughput of
 the fused sm_100a step (tokens already on the device); ``e2e`` is the same
-metric through the public ``ShardEngine.train_step`` API with per-step pinned
+metric through the public ``ShardEngine.train_step_async`` API with per-step pinned
 host -> device input copies and a device -> host read of the step statistics.
 """
 import argparse
@@ -210,21 +210,28 @@ def main():
         pin_tok = [torch.from_numpy(toks[(n_steps + s) * B:(n_steps + s + 1) * B].copy()).pin_memory()
                    for s in range(n_e2e)]
         pin_sid = torch.from_numpy(sid_step.copy()).pin_memory()
+        # software-pipelined by one step, exactly like trainer.train(): queue step s (its pinned-host -> device copy
+        # runs on the copy stream), then read step s-1's statistics (asynchronous D2H into a pinned ring + event)
         for s in range(W):
-            eng.train_step(pin_tok[s], pin_sid, (n_steps + s) * B, 0, args.lr).cpu()
+            eng.train_step_async(pin_tok[s], pin_sid, (n_steps + s) * B, 0, args.lr).result()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2e_pairs = 0.0
+        prev = None
         e0.record()
         for s in range(W, n_e2e):
-            st = eng.train_step(pin_tok[s], pin_sid, (n_steps + s) * B, 0, args.lr).cpu()   # D2H: pairs, loss, ...
-            e2e_pairs += float(st[0])
+            h = eng.train_step_async(pin_tok[s], pin_sid, (n_steps + s) * B, 0, args.lr)   # H2D: tokens + sentence ids
+            if prev is not None:
+                e2e_pairs += float(prev.result()[0])                                     # D2H: pairs, loss, ...
+            prev = h
+        e2e_pairs += float(prev.result()[0])
         e1.record()
         barrier()
         ms2 = max_over_ranks(e0.elapsed_time(e1))
         result["e2e"] = {"value": e2e_pairs / (ms2 * 1e-3), "unit": "pairs/s", "ms_per_step": ms2 / K,
                          "h2d_bytes_per_step": int(B * 4 * 2), "d2h_bytes_per_step": 16,
-                         "api": "ShardEngine.train_step(pinned tokens, pinned sent_id) -> stats.cpu()"}
+                         "api": "ShardEngine.train_step_async(pinned tokens, pinned sent_id) -> handle.result() "
+                                "(every step: H2D of its inputs, D2H of its statistics; read-back lags one step)"}
     sampler.stop()
     sampler.join(timeout=2)
     result["clocks"] = sampler.summary()

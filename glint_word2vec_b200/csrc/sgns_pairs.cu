@@ -31,6 +31,8 @@ constexpr int PK_FP = 8;              // floats per pair in exchange slots (1 + 
 constexpr int PK_BATCH = 4;           // pairs per batch: slot = 32 floats = 128 B
 constexpr int PK_LAG = 16;            // max pairs between pass A and pass B (template parameter LAG: 4 or 16)
 constexpr int PK_NSLOT = 14;          // >= 2 * (batches in flight + 1)
+constexpr int PK_XCHUNKS = 11;        // 16-byte chunks {f, f, f, tag} carrying one batch (4 pairs x 8 dots = 32 floats)
+constexpr int PK_XSTRIDE = 48;        // floats per (slot, source) region: 12 chunks, 192 B
 
 template <int G> __device__ __forceinline__ int pk_row_of_lane(int lane) {
     const int lg = lane & (G - 1);
@@ -194,6 +196,7 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
 struct PkWarpSmem {
     float fdot[2 * PK_LAG * PK_FP];      // partial (then total) dots of the pairs between pass A and pass B
     float xsum[8 * 32];                  // per-source copy of one batch for the ordered reduction
+    int dstash[2 * PK_LAG * 12];         // pair descriptors between pass A and pass B (saves an L2 round trip)
 };
 
 // LAG = pairs between pass A and pass B of a warp.  The rows touched in between must still be in L2 when
@@ -214,6 +217,7 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
     const int warp = threadIdx.x >> 5;
     float* fdot = wsm[warp].fdot;
     float* xsum = wsm[warp].xsum;
+    int* dstash = wsm[warp].dstash;
     const int K = p.K;
     const int n = p.negatives;
     const int S = p.world;
@@ -231,7 +235,7 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
     const int myrow = pk_row_of_lane<G>(lane);
     const bool owner = lg == pk_lane_of_row<G>(myrow);
 
-    const size_t slot_stride = 32;                                               // floats per (slot, source)
+    const size_t slot_stride = PK_XSTRIDE;                                       // floats per (slot, source)
     const size_t warp_x_base = (size_t)gwarp * PK_NSLOT * S * slot_stride;
     uint32_t* my_flags = p.flags[rank] + (size_t)gwarp * S;
     const uint32_t seq0 = warp_seq[gwarp];
@@ -246,6 +250,12 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             PairDesc d;
             pk_load_desc(desc, gvalid ? pair : 0, pd, d);
             const int ctok = d.w[1];
+            if (lg == 0) {
+                int4* st = reinterpret_cast<int4*>(dstash + ((k % RFS) * P + grp) * 12);
+                st[0] = make_int4(d.w[0], d.w[1], d.w[2], d.w[3]);
+                st[1] = make_int4(d.w[4], d.w[5], d.w[6], d.w[7]);
+                st[2] = make_int4(d.w[8], d.w[9], d.w[10], d.w[11]);
+            }
             float u[CHUNKS][4];
             float v[8][CHUNKS][4];
 #pragma unroll
@@ -277,32 +287,34 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             const float tot = pk_reduce8<G>(f, lane);
             if (owner) fdot[((k % RFS) * P + grp) * PK_FP + myrow] = gvalid ? tot : 0.f;
             if ((k + 1) % BS == 0 || k == nk - 1) {
-                // ---- push the batch: lane j -> rank j's slot, then release-publish the sequence number
+                // ---- push the batch.  No fence and no separate flag: every 16-byte chunk carries its own
+                // sequence tag {f, f, f, tag} (one st.v4 = one NVLink write), the receiver polls the data itself.
+                // (A st.release.sys flag costs a membar.sys round trip per batch: it was the top stall reason,
+                // 6.3 stalled warps per issue in profiles/r1_run20_multi_ncu.md.)
                 __syncwarp();
                 const int b = k / BS;
                 const uint32_t bseq = seq0 + (uint32_t)b;
                 const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
-                if (p.xbuf_mc != nullptr) {
-                    // NVLS: ONE multicast store per 16 bytes lands in every rank's slot (switch-replicated),
-                    // then a multicast release-store publishes the sequence number everywhere
-                    const float4* src = reinterpret_cast<const float4*>(fdot + (size_t)((b * BS) % RFS) * P * PK_FP);
-                    float* dstmc = p.xbuf_mc + warp_x_base + ((size_t)slot * S + rank) * slot_stride;
-                    if (lane < 8) {
-                        const float4 x = src[lane];
+                if (lane < PK_XCHUNKS) {
+                    const float* src = fdot + (size_t)((b * BS) % RFS) * P * PK_FP + 3 * lane;
+                    const float x0 = src[0], x1 = src[1], x2 = (3 * lane + 2 < 32) ? src[2] : 0.f;
+                    const uint32_t tag = bseq + 1u;
+                    if (p.xbuf_mc != nullptr) {
+                        // NVLS: one multicast store lands in every rank's slot (switch-replicated)
+                        float* dst = p.xbuf_mc + warp_x_base + ((size_t)slot * S + rank) * slot_stride + 4 * lane;
                         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                                     ::"l"(dstmc + 4 * lane), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+                                     ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(__uint_as_float(tag)) : "memory");
+                    } else {
+                        for (int r = 0; r < S; ++r) {
+                            if (r == rank) continue;
+                            // debug bit 3 (profiling on ONE GPU): every xbuf pointer is this GPU's own buffer and
+                            // the store to "rank r" plays the message FROM rank r, so the kernel feeds itself
+                            const int srcidx = (p.debug & 8) ? r : rank;
+                            float* dst = p.xbuf[r] + warp_x_base + ((size_t)slot * S + srcidx) * slot_stride + 4 * lane;
+                            asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                         ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(__uint_as_float(tag)) : "memory");
+                        }
                     }
-                    __syncwarp();
-                    if (lane == 0)
-                        asm volatile("multimem.st.release.sys.global.b32 [%0], %1;"
-                                     ::"l"(p.flags_mc + (size_t)gwarp * S + rank), "r"(bseq + 1u) : "memory");
-                } else if (lane < S && lane != rank) {
-                    float4* dst = reinterpret_cast<float4*>(p.xbuf[lane] + warp_x_base +
-                                                            ((size_t)slot * S + rank) * slot_stride);
-                    const float4* src = reinterpret_cast<const float4*>(fdot + (size_t)((b * BS) % RFS) * P * PK_FP);
-#pragma unroll
-                    for (int v4 = 0; v4 < 8; ++v4) dst[v4] = src[v4];
-                    st_release_sys(p.flags[lane] + (size_t)gwarp * S + rank, bseq + 1u);
                 }
                 __syncwarp();
             }
@@ -315,30 +327,36 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 const uint32_t bseq = seq0 + (uint32_t)b;
                 const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
                 float* mine = fdot + (size_t)((b * BS) % RFS) * P * PK_FP;       // 32 floats of this batch
-                if (lane < S && lane != rank) {
+                {
+                    const uint32_t tag = bseq + 1u;
                     unsigned long long t0 = p.timing ? globaltimer_ns() : 0ull;
-                    uint32_t spins = 0;
-                    volatile uint32_t* fl = my_flags + lane;
-                    while ((int32_t)(*fl - (bseq + 1u)) < 0) {
-                        if ((++spins & 0x3FFFu) == 0) {
-                            if (t0 == 0ull) t0 = globaltimer_ns();
-                            if (globaltimer_ns() - t0 > 20000000000ull) {
-                                printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u (flag %u)\n",
-                                       rank, gwarp, lane, bseq + 1u, *fl);
-                                atomicExch(p.error_flag, 1);
-                                __trap();
+                    // (S-1) sources x 11 chunks, strided over the lanes; each chunk is polled until its tag matches
+                    for (int it = lane; it < (S - 1) * PK_XCHUNKS; it += 32) {
+                        const int q = it / PK_XCHUNKS, c = it - q * PK_XCHUNKS;
+                        const int srcr = q + (q >= rank ? 1 : 0);
+                        const float* ptr = p.xbuf[rank] + warp_x_base + ((size_t)slot * S + srcr) * slot_stride + 4 * c;
+                        uint32_t g0, g1, g2, g3, spins = 0;
+                        unsigned long long tw = 0ull;
+                        while (true) {
+                            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "l"(ptr) : "memory");
+                            if (g3 == tag) break;
+                            if ((++spins & 0x3FFFu) == 0) {
+                                if (tw == 0ull) tw = globaltimer_ns();
+                                if (globaltimer_ns() - tw > 20000000000ull) {
+                                    printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u (tag %u)\n",
+                                           rank, gwarp, srcr, tag, g3);
+                                    atomicExch(p.error_flag, 1);
+                                    __trap();
+                                }
                             }
                         }
+                        float* xs = xsum + srcr * 32 + 3 * c;
+                        xs[0] = __uint_as_float(g0);
+                        xs[1] = __uint_as_float(g1);
+                        if (3 * c + 2 < 32) xs[2] = __uint_as_float(g2);
                     }
-                    (void)ld_acquire_sys(my_flags + lane);      // acquire: the peer's data stores are visible
                     if (p.timing) wait_ns += globaltimer_ns() - t0;
-                    const float4* src = reinterpret_cast<const float4*>(
-                        p.xbuf[rank] + warp_x_base + ((size_t)slot * S + lane) * slot_stride);
-                    float4 got[8];
-#pragma unroll
-                    for (int v4 = 0; v4 < 8; ++v4) got[v4] = __ldcg(src + v4);
-#pragma unroll
-                    for (int v4 = 0; v4 < 8; ++v4) reinterpret_cast<float4*>(xsum + lane * 32)[v4] = got[v4];
                 }
                 xsum[rank * 32 + lane] = mine[lane];
                 __syncwarp();
@@ -350,7 +368,13 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             const long long pair = ((long long)gwarp + (long long)kb * n_warps) * P + grp;
             const bool gvalid = pair < n_pairs;
             PairDesc d;
-            pk_load_desc(desc, gvalid ? pair : 0, pd, d);
+            {
+                const int4* st = reinterpret_cast<const int4*>(dstash + ((kb % RFS) * P + grp) * 12);
+                const int4 a = st[0], b2 = st[1], c2 = st[2];
+                d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+                d.w[4] = b2.x; d.w[5] = b2.y; d.w[6] = b2.z; d.w[7] = b2.w;
+                d.w[8] = c2.x; d.w[9] = c2.y; d.w[10] = c2.z; d.w[11] = c2.w;
+            }
             const int ctok = d.w[1];
             float* urow = p.syn0 + (size_t)d.w[0] * K;
             float u[CHUNKS][4], du[CHUNKS][4];
@@ -488,7 +512,7 @@ int sgns_pairs_grid(int K, int device, bool multi) {
 void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats) {
     *warps_per_cta = PK_THREADS / 32;
     *nslot = PK_NSLOT;
-    *slot_floats = 32;
+    *slot_floats = PK_XSTRIDE;
 }
 
 void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid, cudaStream_t stream) {

@@ -59,6 +59,14 @@ class EngineOptions:
         return cls(**known)
 
 
+class _ReadyHandle:
+    def __init__(self, value):
+        self._value = value
+
+    def result(self):
+        return torch.as_tensor(self._value)
+
+
 class ShardEngine:
     def __init__(self, cfg: SGNSConfig, comm: Optional[Comm] = None,
                  device: Optional[torch.device] = None, options: Optional[EngineOptions] = None):
@@ -156,6 +164,18 @@ class ShardEngine:
             return self._cuda.train_step(tokens, sent_id, raw_pos0, iteration, alpha)
         return self._train_step_cpu(np.asarray(tokens, dtype=np.int32), np.asarray(sent_id, dtype=np.int32),
                                     raw_pos0, iteration, alpha)
+
+    def train_step_async(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float):
+        """``train_step`` whose statistics are read back asynchronously: returns a handle with
+        ``result() -> CPU tensor``.  On GPUs the host -> device copy of the NEXT step and the read-back of
+        the PREVIOUS one overlap this step's kernels (``ops/cuda.py::train_step_async``)."""
+        if self.alias is None:
+            raise RuntimeError("set_noise() must be called before training")
+        self._norms = None
+        if self.is_cuda:
+            return self._cuda.train_step_async(tokens, sent_id, raw_pos0, iteration, alpha)
+        return _ReadyHandle(self._train_step_cpu(np.asarray(tokens, dtype=np.int32),
+                                                 np.asarray(sent_id, dtype=np.int32), raw_pos0, iteration, alpha))
 
     def _train_step_cpu(self, tokens, sent_id, raw_pos0, iteration, alpha):
         cfg = self.cfg

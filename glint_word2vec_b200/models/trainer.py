@@ -92,7 +92,7 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
                 continue
             alpha = sgns.learning_rate(learning_rate, words_prev + words_it, total_words)
             with nvtx_range("sgns_step"):
-                stats = engine.train_step(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
+                stats = engine.train_step_async(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
             pending.append(stats)
             words_it += batch.n_words
             rep.steps += 1
@@ -116,8 +116,9 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
 def _drain(pending, rep: TrainReport, alpha, words, mf):
     if not pending:
         return
-    st = torch.stack([p.to("cpu", torch.float64) if isinstance(p, torch.Tensor) else torch.tensor(p)
-                      for p in pending])
+    vals = [p.result() if hasattr(p, "result") else p for p in pending]      # async step handles
+    st = torch.stack([v.to("cpu", torch.float64) if isinstance(v, torch.Tensor) else torch.tensor(v, dtype=torch.float64)
+                      for v in vals])
     pending.clear()
     pairs = int(st[:, 0].sum())
     loss = float(st[:, 1].sum())

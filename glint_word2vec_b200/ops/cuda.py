@@ -32,6 +32,34 @@ def extension():
     return _C
 
 
+N_STAGE = 4                 # input staging slots (host may run this many steps ahead before blocking)
+STATS_RING = 256            # in-flight asynchronous statistics read-backs
+
+
+class _StageSlot:
+    def __init__(self, cap: int, dev):
+        self.pin_tok = torch.empty(cap, dtype=torch.int32).pin_memory()
+        self.pin_sid = torch.empty(cap, dtype=torch.int32).pin_memory()
+        self.tok = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.sid = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.h2d_ev = torch.cuda.Event()
+        self.free_ev = None
+
+
+class StepHandle:
+    """Result of an asynchronous step: ``result()`` -> CPU tensor ``[pairs, loss, max|dot|, kept_tokens]``."""
+
+    def __init__(self, ring, ev, j):
+        self._ring, self._ev, self._j = ring, ev, j
+        self._val = None
+
+    def result(self) -> torch.Tensor:
+        if self._val is None:
+            self._ev.synchronize()
+            self._val = self._ring[self._j].clone()
+        return self._val
+
+
 class CudaShardOps:
     """GPU state + kernels of one ``ShardEngine``."""
 
@@ -43,6 +71,11 @@ class CudaShardOps:
         self.K = engine.shard.cols
         self.world = engine.comm.world
         self.rank = engine.comm.rank
+        # profiling only: run the column-shard kernel of a pretended world of S on ONE GPU (its pushes land in
+        # its own buffer, see sgns_pairs.cu debug bit 3) so that ncu / quick sweeps do not need a multi-GPU box
+        self._loopback = int(os.environ.get("GW2V_LOOPBACK_WORLD", "0")) if engine.comm.world == 1 else 0
+        if self._loopback > 1:
+            self.world = self._loopback
         self.alias_dev: Optional[torch.Tensor] = None
         self.keep_dev: Optional[torch.Tensor] = None
         self.subsample_active = True
@@ -57,15 +90,19 @@ class CudaShardOps:
         self.launches = 0                    # kernel launches issued by this object (bench bookkeeping)
         self._count_val = -1
         self.debug = int(os.environ.get("GW2V_DEBUG", "0"))      # profiling-only kernel switches
+        if self._loopback > 1:
+            self.debug |= 8
         # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self.exp_table = None
         if engine.cfg.sigmoid_mode == "table":
             from ..models.sgns import _exp_table
             self.exp_table = _exp_table().to(self.dev).contiguous()
         self._props = torch.cuda.get_device_properties(self.dev)
+        self._copy_stream = None
+        self._stage = []
         # world > 1: serving collectives are fused into the kernels (ops/serving.py); GW2V_SERVE_FUSED=0 falls
         # back to kernel + NCCL collective (kept for A/B measurements)
-        self.serve_fused = self.world > 1 and os.environ.get("GW2V_SERVE_FUSED", "1") != "0"
+        self.serve_fused = engine.comm.world > 1 and os.environ.get("GW2V_SERVE_FUSED", "1") != "0"
         self._serve = None
 
     # ------------------------------------------------------------------ setup
@@ -93,15 +130,22 @@ class CudaShardOps:
             return
         cap = max(t, 1024)
         d = self.dev
-        self.tok_in = torch.empty(cap, dtype=torch.int32, device=d)
-        self.sid_in = torch.empty(cap, dtype=torch.int32, device=d)
+        if self._cap > 0:
+            torch.cuda.synchronize(d)             # growing: earlier steps may still be using the old buffers
+        # staging ring: pinned host buffer + device buffer + events per slot, so the host can run ahead of the
+        # device (trainer.train queues up to 64 steps) without overwriting a pinned buffer whose H2D is pending
+        self._stage = [_StageSlot(cap, d) for _ in range(N_STAGE)]
+        self._stage_i = -1
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=d)
+            self._pin_stats = torch.zeros(STATS_RING, 4, dtype=torch.float32).pin_memory()
+            self._stats_ev = [None] * STATS_RING
+            self._stats_j = -1
         self.tok_c = torch.empty(cap, dtype=torch.int32, device=d)
         self.sid_c = torch.empty(cap, dtype=torch.int32, device=d)
         self.count = torch.zeros(1, dtype=torch.int32, device=d)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=d)
         self.chain = torch.zeros(int(_C.subsample_max_blocks(cap)) + 1, dtype=torch.int64, device=d)
-        self.pin_tok = torch.empty(cap, dtype=torch.int32).pin_memory()
-        self.pin_sid = torch.empty(cap, dtype=torch.int32).pin_memory()
         self._stats_ring = torch.zeros(256, 4, dtype=torch.float32, device=d)
         self._count_val = -1
         # pair-generation workspaces (pairgen.cu)
@@ -152,14 +196,21 @@ class CudaShardOps:
             units = grid                              # one exchange ring (2 slots) per CTA
             xbytes = units * 2 * self.world * slot_floats * 4
             nseq = grid
-        # all ranks must launch the identical geometry (the flag protocol pairs warp w with warp w)
-        g = torch.tensor([grid, -grid], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(g, op=dist.ReduceOp.MIN, group=self.e.comm.group)
-        if int(g[0].item()) != grid or int(-g[1].item()) != grid:
-            raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
         fbytes = (units * self.world * 4 + 255) // 256 * 256
         xbytes = (xbytes + 255) // 256 * 256
-        buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
+        if self._loopback > 1:
+            if variant != 3:
+                raise RuntimeError("GW2V_LOOPBACK_WORLD supports the pairs kernel only")
+            from ..parallel.symm import SymmBuffer
+            local = torch.zeros(xbytes + fbytes, dtype=torch.uint8, device=self.dev)
+            buf = SymmBuffer(local, [local.data_ptr()] * self.world, 0, None)
+        else:
+            # all ranks must launch the identical geometry (the flag protocol pairs warp w with warp w)
+            g = torch.tensor([grid, -grid], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(g, op=dist.ReduceOp.MIN, group=self.e.comm.group)
+            if int(g[0].item()) != grid or int(-g[1].item()) != grid:
+                raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
+            buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
         self._xchg = {
             "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats, "variant": variant,
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
@@ -173,26 +224,55 @@ class CudaShardOps:
         self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
 
     # ------------------------------------------------------------------ training
-    def stage_tokens(self, tokens, sent_id) -> int:
-        """Host -> device copy of one step's inputs through pinned memory."""
+    def stage_tokens(self, tokens, sent_id):
+        """Host -> device copy of one step's inputs on the copy stream (overlaps the previous step's kernels).
+        Returns ``(slot, t)``.  The host blocks only when it is ``N_STAGE`` steps ahead of the device."""
         t = int(len(tokens))
         self._ensure_capacity(t)
-        if isinstance(tokens, torch.Tensor) and tokens.is_pinned():
-            self.tok_in[:t].copy_(tokens, non_blocking=True)
-            self.sid_in[:t].copy_(sent_id, non_blocking=True)
+        self._stage_i = (self._stage_i + 1) % N_STAGE
+        slot = self._stage[self._stage_i]
+        if slot.free_ev is not None:
+            slot.free_ev.synchronize()            # previous user of this slot (H2D + kernels) has finished
+        if isinstance(tokens, torch.Tensor) and tokens.is_pinned() and isinstance(sent_id, torch.Tensor) \
+                and sent_id.is_pinned():
+            src_tok, src_sid = tokens, sent_id
         else:
-            self.pin_tok[:t].copy_(torch.as_tensor(np.ascontiguousarray(tokens, dtype=np.int32)))
-            self.pin_sid[:t].copy_(torch.as_tensor(np.ascontiguousarray(sent_id, dtype=np.int32)))
-            self.tok_in[:t].copy_(self.pin_tok[:t], non_blocking=True)
-            self.sid_in[:t].copy_(self.pin_sid[:t], non_blocking=True)
-        return t
+            slot.pin_tok[:t].copy_(torch.as_tensor(np.ascontiguousarray(tokens, dtype=np.int32)))
+            slot.pin_sid[:t].copy_(torch.as_tensor(np.ascontiguousarray(sent_id, dtype=np.int32)))
+            src_tok, src_sid = slot.pin_tok[:t], slot.pin_sid[:t]
+        cs = self._copy_stream
+        with torch.cuda.stream(cs):
+            slot.tok[:t].copy_(src_tok, non_blocking=True)
+            slot.sid[:t].copy_(src_sid, non_blocking=True)
+            slot.h2d_ev.record(cs)
+        return self._stage_i, t
 
     def train_step(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float) -> torch.Tensor:
-        t = self.stage_tokens(tokens, sent_id)
-        return self.train_step_staged(t, raw_pos0, iteration, alpha)
+        si, t = self.stage_tokens(tokens, sent_id)
+        return self.train_step_staged(si, t, raw_pos0, iteration, alpha)
 
-    def train_step_staged(self, t: int, raw_pos0: int, iteration: int, alpha: float) -> torch.Tensor:
-        return self.train_step_device(self.tok_in, self.sid_in, t, raw_pos0, iteration, alpha)
+    def train_step_staged(self, si: int, t: int, raw_pos0: int, iteration: int, alpha: float) -> torch.Tensor:
+        slot = self._stage[si]
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(slot.h2d_ev)
+        stats = self.train_step_device(slot.tok, slot.sid, t, raw_pos0, iteration, alpha)
+        if slot.free_ev is None:
+            slot.free_ev = torch.cuda.Event()
+        slot.free_ev.record(cur)
+        return stats
+
+    def train_step_async(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float) -> "StepHandle":
+        """Like ``train_step`` but the statistics come back through an asynchronous D2H copy into a pinned
+        ring; ``handle.result()`` waits for THIS step only, so a caller that reads step s-1 after queueing
+        step s keeps the device busy (H2D of s+1 and the read of s-1 both overlap the kernels of s)."""
+        stats = self.train_step(tokens, sent_id, raw_pos0, iteration, alpha)
+        self._stats_j = (self._stats_j + 1) % STATS_RING
+        j = self._stats_j
+        if self._stats_ev[j] is None:
+            self._stats_ev[j] = torch.cuda.Event()
+        self._pin_stats[j].copy_(stats, non_blocking=True)
+        self._stats_ev[j].record(torch.cuda.current_stream(self.dev))
+        return StepHandle(self._pin_stats, self._stats_ev[j], j)
 
     def train_step_device(self, tok_dev: torch.Tensor, sid_dev: torch.Tensor, t: int, raw_pos0: int,
                           iteration: int, alpha: float) -> torch.Tensor:

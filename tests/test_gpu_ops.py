@@ -187,6 +187,28 @@ def test_sgns_step_hot_rows_hogwild_close():
     assert cos > 0.5 and 0.1 < float(upd.norm() / ref_upd.norm()) < 10.0
 
 
+def test_async_steps_stage_inputs_safely():
+    """The host queues many steps ahead of the device (trainer.train does): every step must train on ITS OWN
+    tokens - pinned staging buffers are a ring guarded by events, never overwritten while an H2D is pending.
+    Pair counts are a pure function of (positions, sentence ids), so a clobbered buffer shows up exactly."""
+    dev = _dev()
+    v, d = 50000, 64
+    eng, _ = _make_engine(dev, v, d)
+    rng = np.random.default_rng(5)
+    steps = []
+    for s in range(40):
+        t = int(rng.integers(2000, 30000))
+        tokens = rng.integers(0, v, size=t).astype(np.int32)
+        sid = (np.arange(t) // int(rng.integers(3, 60))).astype(np.int32)
+        steps.append((tokens, sid, 1000 * s))
+    handles = [eng.train_step_async(tok, sid, pos0, 0, 0.001) for tok, sid, pos0 in steps]     # no sync in between
+    for (tok, sid, pos0), h in zip(steps, handles):
+        ci, _, _ = sgns.enumerate_pairs(eng.cfg, tok, sid, pos0, 0)
+        st = h.result()
+        assert int(st[0]) == len(ci)
+        assert int(st[3]) == len(tok)
+
+
 def test_zero_pair_step_is_noop():
     dev = _dev()
     eng, _ = _make_engine(dev, 1000, 64)
