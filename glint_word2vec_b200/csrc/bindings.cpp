@@ -150,7 +150,8 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                          reinterpret_cast<uint32_t*>(cinfo.data_ptr<int>()), pair_off.data_ptr<int>(),
                          n_pairs.data_ptr<int>(), desc.data_ptr<int>(),
                          reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()),
-                         reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch, cur_stream());
+                         reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch,
+                         stats.data_ptr<float>(), cur_stream());
     if (world > 1) {
         TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
         TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
@@ -183,6 +184,8 @@ void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thre
     CHECK_CUDA(tok_in); CHECK_DT(tok_in, torch::kInt32); CHECK_DT(sid_in, torch::kInt32);
     CHECK_DT(keep_thresh, torch::kInt32); CHECK_DT(chain, torch::kInt64); CHECK_DT(ticket, torch::kInt32);
     TORCH_CHECK(chain.numel() >= gw2v::subsample_max_blocks((int)T), "chain buffer too small");
+    TORCH_CHECK(T <= gw2v::subsample_max_tokens(), "step too large for the sub-sampling scan (max ",
+                gw2v::subsample_max_tokens(), " tokens)");
     TORCH_CHECK(tok_out.numel() >= T && sid_out.numel() >= T, "output buffers too small");
     c10::cuda::CUDAGuard guard(tok_in.device());
     gw2v::launch_subsample_compact(

@@ -12,6 +12,7 @@ void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const
                               unsigned int* ticket, unsigned long long* chain, uint32_t epoch,
                               cudaStream_t stream);
 int subsample_max_blocks(int max_tokens);
+int subsample_max_tokens();
 void launch_zipf_stream(const int2* alias, int vocab, uint32_t seed_lo, uint32_t seed_hi,
                         unsigned long long pos0, int n, int* out, cudaStream_t stream);
 void launch_init_syn0(float* syn0, long long vocab, int K, int col_start, int vector_size, uint32_t seed_lo,
@@ -24,7 +25,8 @@ int pairgen_max_tokens();
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
                     int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, unsigned int* ticket, unsigned long long* chain, uint32_t epoch, cudaStream_t stream);
+                    int* desc, unsigned int* ticket, unsigned long long* chain, uint32_t epoch, float* stats,
+                    cudaStream_t stream);   // stats (4 floats, may be null) is zeroed by the scan kernel
 
 // infer_kernels.cu
 void launch_gather_rows(const float* syn0, const long long* rows, int R, int K, float* out, cudaStream_t s);

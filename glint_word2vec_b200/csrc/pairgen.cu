@@ -20,7 +20,7 @@
 namespace gw2v {
 
 constexpr int PC_THREADS = 256;
-constexpr int PC_ITEMS = 4;
+constexpr int PC_ITEMS = 2;          // 512-centre tiles: 256 CTAs for a 131 k-token step (4 items left 128 CTAs on 148 SMs)
 constexpr int PC_TILE = PC_THREADS * PC_ITEMS;
 
 // cinfo[i] = valid-context bitmask (bits 0..23, bit q <-> offset lo + q) | (-lo) << 24
@@ -86,7 +86,8 @@ pair_count_kernel(const int* __restrict__ tokens, const int* __restrict__ sent_i
 
 // exclusive scan of the (<= 1024) tile sums by one CTA; writes the total pair count
 __global__ void __launch_bounds__(1024)
-pair_tile_scan_kernel(int* __restrict__ tile_sum, int ntiles, int* __restrict__ n_pairs) {
+pair_tile_scan_kernel(int* __restrict__ tile_sum, int ntiles, int* __restrict__ n_pairs, float* __restrict__ stats) {
+    if (stats != nullptr && threadIdx.x < 4) stats[threadIdx.x] = 0.f;      // step statistics start at zero
     __shared__ int wt[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int v = tid < ntiles ? tile_sum[tid] : 0;
@@ -132,11 +133,24 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     const int ncalls = (negatives + 1) >> 1;
     const uint32_t sw = stream_word(STREAM_NEG, iteration);
     const int slot = off + window;
-    for (int c = 0; c < ncalls; ++c) {
-        uint4 r = rand4(seed_lo, seed_hi, sw, pos0 + (unsigned long long)i, (uint32_t)(slot * ncalls + c));
-        e[2 + 2 * c] = alias_sample(alias, (uint32_t)vocab, r.x, r.y);
-        if (2 * c + 1 < negatives) e[2 + 2 * c + 1] = alias_sample(alias, (uint32_t)vocab, r.z, r.w);
+    // all Philox calls first, then all alias-table reads in flight together (they are independent random
+    // 8-byte reads into an 80 MB table), then the selects - the serial version cost 28 us per step
+    uint32_t idx[8], sel[8];
+    int2 ent[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (c < ncalls) {
+            const uint4 r = rand4(seed_lo, seed_hi, sw, pos0 + (unsigned long long)i, (uint32_t)(slot * ncalls + c));
+            idx[2 * c] = __umulhi(r.x, (uint32_t)vocab); sel[2 * c] = r.y;
+            idx[2 * c + 1] = __umulhi(r.z, (uint32_t)vocab); sel[2 * c + 1] = r.w;
+        }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < negatives) ent[j] = __ldg(alias + idx[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < negatives) e[2 + j] = (sel[j] < (uint32_t)ent[j].x) ? (int)idx[j] : ent[j].y;
 }
 
 int pairgen_max_blocks(int max_tokens) { return (max_tokens + PC_TILE - 1) / PC_TILE + 1; }
@@ -150,13 +164,17 @@ void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, 
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
                     int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
                     int* desc, unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
-                    cudaStream_t stream) {
-    if (max_tokens <= 0) { cudaMemsetAsync(n_pairs, 0, sizeof(int), stream); return; }
+                    float* stats, cudaStream_t stream) {
+    if (max_tokens <= 0) {
+        cudaMemsetAsync(n_pairs, 0, sizeof(int), stream);
+        if (stats) cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream);
+        return;
+    }
     const int grid = (max_tokens + PC_TILE - 1) / PC_TILE;          // <= 1024 (checked by the binding)
     int* tile_sum = reinterpret_cast<int*>(chain);                   // reuse the workspace: >= grid ints
     pair_count_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration, pos0,
                                                        window, window_mode, cinfo, pair_off, tile_sum);
-    pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, n_pairs);
+    pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, n_pairs, stats);
     const int slots = 2 * window + 1;
     const long long total = (long long)max_tokens * slots;
     pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, tile_sum,

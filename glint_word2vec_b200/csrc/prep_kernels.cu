@@ -11,7 +11,7 @@
 namespace gw2v {
 
 constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
+constexpr int SC_ITEMS = 2;          // 512-token tiles: 256 CTAs for a 131 k-token step (8 items left 64 CTAs on 148 SMs)
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
 __device__ __forceinline__ bool sc_keep(const int* __restrict__ tok_in, const uint32_t* __restrict__ keep_thresh,
@@ -124,7 +124,7 @@ void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const
                               unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
                               cudaStream_t stream) {
     if (T <= 0) { cudaMemsetAsync(count_out, 0, sizeof(int), stream); return; }
-    const int grid = (T + SC_TILE - 1) / SC_TILE;                  // <= 1024 tiles (2M tokens per step)
+    const int grid = (T + SC_TILE - 1) / SC_TILE;                  // <= 1024 tiles (512 k tokens per step)
     int* tile_sum = reinterpret_cast<int*>(chain);
     subsample_count_kernel<<<grid, SC_THREADS, 0, stream>>>(tok_in, T, keep_thresh, seed_lo, seed_hi, iteration,
                                                             raw_pos0, tile_sum);
@@ -133,6 +133,7 @@ void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const
                                                               iteration, raw_pos0, tile_sum, tok_out, sid_out);
 }
 
+int subsample_max_tokens() { return 1024 * SC_TILE; }
 int subsample_max_blocks(int max_tokens) { return (max_tokens + SC_TILE - 1) / SC_TILE + 1; }
 
 // ---------------------------------------------------------------------------

@@ -203,6 +203,8 @@ struct PkWarpSmem {
 // pass B re-gathers them: in-flight footprint = LAG x warps x (2+n) rows.  LAG 16 at K=256 is 265 MB (> the
 // 126 MB L2, pass B then re-reads DRAM: measured 1.21 ms vs 0.62 ms for the exchange-free kernel); one batch
 // (LAG 4, ~35 us of work per warp) already covers the ~2-3 us NVLink round trip many times over.
+// (Issuing pass B's row re-gather BEFORE pass A of the same iteration - to overlap its L2 latency with pass A's
+// DRAM gathers - was measured and is slower at every occupancy: K=64 0.332 -> 0.398 ms, K=128 0.507 -> 0.694 ms.)
 template <int G, int CHUNKS, int MINB, int LAG>
 __global__ void __launch_bounds__(PK_THREADS, MINB)
 sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr,
@@ -243,6 +245,39 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
     unsigned long long wait_ns = 0;
 
     for (int k = 0; k < nk + LAGS; ++k) {
+        const int kb = k - LAGS;
+        // ---- pass B operands (descriptor from the shared-memory stash, rows re-gathered from L2)
+        PairDesc dB;
+        bool gvalidB = false;
+        float uB[CHUNKS][4];
+        float vB[8][CHUNKS][4];
+        bool ractB[8];
+        auto load_b = [&]() {
+            const long long pairB = ((long long)gwarp + (long long)kb * n_warps) * P + grp;
+            gvalidB = pairB < n_pairs;
+            const int4* st = reinterpret_cast<const int4*>(dstash + ((kb % RFS) * P + grp) * 12);
+            const int4 a = st[0], b2 = st[1], c2 = st[2];
+            dB.w[0] = a.x; dB.w[1] = a.y; dB.w[2] = a.z; dB.w[3] = a.w;
+            dB.w[4] = b2.x; dB.w[5] = b2.y; dB.w[6] = b2.z; dB.w[7] = b2.w;
+            dB.w[8] = c2.x; dB.w[9] = c2.y; dB.w[10] = c2.z; dB.w[11] = c2.w;
+            const int ctokB = dB.w[1];
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                for (int el = 0; el < 4; ++el) uB[c][el] = 0.f;
+                if (gvalidB && act[c]) pk_ld4(p.syn0 + (size_t)dB.w[0] * K + coff[c], uB[c]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                ractB[r] = gvalidB && r <= n && (r == 0 || dB.w[r + 1] != ctokB);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) vB[r][c][el] = 0.f;
+                    if (ractB[r] && act[c]) pk_ld4(p.syn1 + (size_t)dB.w[r + 1] * K + coff[c], vB[r][c]);
+                }
+            }
+        };
         if (k < nk) {
             // ------------------------------------------------------------ pass A: partial dots of step k
             const long long pair = ((long long)gwarp + (long long)k * n_warps) * P + grp;
@@ -295,6 +330,12 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 const int b = k / BS;
                 const uint32_t bseq = seq0 + (uint32_t)b;
                 const int slot = (int)(bseq % (uint32_t)PK_NSLOT);
+                if (p.debug & 16) {
+                    // protocol stress test: pseudo-random delay (0-16 us) per warp, batch and rank before the push,
+                    // so ranks drift by many batches and the slot ring / tags are exercised out of lock-step
+                    const uint32_t h = ((uint32_t)gwarp * 2654435761u) ^ (bseq * 40503u) ^ ((uint32_t)rank * 0x9E3779B9u);
+                    __nanosleep((h >> 9) & 0x3FFFu);
+                }
                 if (lane < PK_XCHUNKS) {
                     const float* src = fdot + (size_t)((b * BS) % RFS) * P * PK_FP + 3 * lane;
                     const float x0 = src[0], x1 = src[1], x2 = (3 * lane + 2 < 32) ? src[2] : 0.f;
@@ -319,7 +360,6 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 __syncwarp();
             }
         }
-        const int kb = k - LAGS;
         if (kb >= 0) {
             // ------------------------------------------------------------ pass B: reduce + update step kb
             if (kb % BS == 0) {
@@ -365,37 +405,18 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 mine[lane] = tot;
                 __syncwarp();
             }
-            const long long pair = ((long long)gwarp + (long long)kb * n_warps) * P + grp;
-            const bool gvalid = pair < n_pairs;
-            PairDesc d;
-            {
-                const int4* st = reinterpret_cast<const int4*>(dstash + ((kb % RFS) * P + grp) * 12);
-                const int4 a = st[0], b2 = st[1], c2 = st[2];
-                d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
-                d.w[4] = b2.x; d.w[5] = b2.y; d.w[6] = b2.z; d.w[7] = b2.w;
-                d.w[8] = c2.x; d.w[9] = c2.y; d.w[10] = c2.z; d.w[11] = c2.w;
-            }
-            const int ctok = d.w[1];
+            load_b();
+            const PairDesc& d = dB;
+            const bool gvalid = gvalidB;
             float* urow = p.syn0 + (size_t)d.w[0] * K;
-            float u[CHUNKS][4], du[CHUNKS][4];
-            float v[8][CHUNKS][4];
-            bool ract[8];
+            float du[CHUNKS][4];
 #pragma unroll
-            for (int c = 0; c < CHUNKS; ++c) {
+            for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
-                for (int el = 0; el < 4; ++el) { u[c][el] = 0.f; du[c][el] = 0.f; }
-                if (gvalid && act[c]) pk_ld4(urow + coff[c], u[c]);
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                ract[r] = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
-#pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) {
-#pragma unroll
-                    for (int el = 0; el < 4; ++el) v[r][c][el] = 0.f;
-                    if (ract[r] && act[c]) pk_ld4(p.syn1 + (size_t)d.w[r + 1] * K + coff[c], v[r][c]);
-                }
-            }
+                for (int el = 0; el < 4; ++el) du[c][el] = 0.f;
+            auto& u = uB;
+            auto& v = vB;
+            auto& ract = ractB;
             const float fm = fdot[((kb % RFS) * P + grp) * PK_FP + myrow];
             unsigned actmask = 0;
 #pragma unroll
@@ -472,14 +493,21 @@ static int pk_lag() {
     return lag;
 }
 
+// kernel variant selection for the column-shard kernel: LAG in {4, 16}
+template <int GG, int C, int MB, typename F>
+static void pk_multi_select(F&& f) {
+    if (pk_lag() >= 16) f(sgns_pairs_multi_kernel<GG, C, MB, 16>);
+    else f(sgns_pairs_multi_kernel<GG, C, MB, 4>);
+}
+
 #define GW2V_PK_DISPATCH(K, CALL)                                            \
     do {                                                                     \
         int G_, ch_;                                                         \
         pk_group((K), &G_, &ch_);                                            \
-        const bool o4 = pk_occ() >= 4;                                       \
-        if (G_ == 8) { if (o4) CALL(8, 1, 4); else CALL(8, 1, 3); }          \
-        else if (G_ == 16) { if (o4) CALL(16, 1, 4); else CALL(16, 1, 3); }  \
-        else if (ch_ == 1) { if (o4) CALL(32, 1, 4); else CALL(32, 1, 3); }  \
+        const int o_ = pk_occ();                                             \
+        if (G_ == 8) { if (o_ >= 4) CALL(8, 1, 4); else if (o_ == 3) CALL(8, 1, 3); else CALL(8, 1, 2); }        \
+        else if (G_ == 16) { if (o_ >= 4) CALL(16, 1, 4); else if (o_ == 3) CALL(16, 1, 3); else CALL(16, 1, 2); } \
+        else if (ch_ == 1) { if (o_ >= 4) CALL(32, 1, 4); else if (o_ == 3) CALL(32, 1, 3); else CALL(32, 1, 2); } \
         else if (ch_ == 2) { CALL(32, 2, 2); }                               \
         else if (ch_ == 3) { CALL(32, 3, 1); }                               \
         else if (ch_ == 4) { CALL(32, 4, 1); }                               \
@@ -491,13 +519,8 @@ int sgns_pairs_grid(int K, int device, bool multi) {
     int sms = 148, occ = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (multi) {
-#define CALL(GG, C, MB)                                                                                              \
-    do {                                                                                                             \
-        if (pk_lag() >= 16)                                                                                          \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB, 16>, PK_THREADS, 0); \
-        else                                                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sgns_pairs_multi_kernel<GG, C, MB, 4>, PK_THREADS, 0);  \
-    } while (0)
+#define CALL(GG, C, MB) pk_multi_select<GG, C, MB>([&](auto kern) {                      \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PK_THREADS, 0); })
         GW2V_PK_DISPATCH(K, CALL);
 #undef CALL
     } else {
@@ -523,13 +546,8 @@ void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs,
 
 void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
                              uint32_t* warp_seq, cudaStream_t stream) {
-#define CALL(GG, C, MB)                                                                                        \
-    do {                                                                                                       \
-        if (pk_lag() >= 16)                                                                                    \
-            sgns_pairs_multi_kernel<GG, C, MB, 16><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq); \
-        else                                                                                                   \
-            sgns_pairs_multi_kernel<GG, C, MB, 4><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq);  \
-    } while (0)
+#define CALL(GG, C, MB) pk_multi_select<GG, C, MB>([&](auto kern) {                      \
+        kern<<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq); })
     GW2V_PK_DISPATCH(p.K, CALL);
 #undef CALL
 }

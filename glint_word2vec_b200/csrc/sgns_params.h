@@ -24,7 +24,8 @@ struct SgnsParams {
     float alpha, max_grad;
     const float* exp_table;      // 1000-entry sigma table on [-6,6] (MLLIB:281-302 parity mode) or null = exact
     int compute_loss;
-    int debug;                   // profiling only: bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads
+    int debug;                   // bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads (profiling);
+                                 // bit3 single-GPU loopback of the exchange (profiling); bit4 random push delays (stress test)
     // ---- cross-shard exchange (world > 1)
     int world, rank;
     int tile_centers;            // centres per CTA tile

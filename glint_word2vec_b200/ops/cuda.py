@@ -297,7 +297,10 @@ class CudaShardOps:
             tok, sid = tok_dev, sid_dev
         self._stats_i = (self._stats_i + 1) % self._stats_ring.shape[0]
         stats = self._stats_ring[self._stats_i]
-        stats.zero_()
+        pairs_path = (self.world > 1 and self._xchg["variant"] == 3) or \
+            (self.world == 1 and getattr(self, "_variant", None) == 3)
+        if not pairs_path:
+            stats.zero_()                 # the pairs path zeroes them inside pair_tile_scan_kernel (one launch less)
         wm = WINDOW_MODES[cfg.window_mode]
         if self.world > 1 and self._xchg["variant"] == 3:
             x = self._xchg

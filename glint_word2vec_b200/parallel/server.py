@@ -305,9 +305,31 @@ def main(argv=None):
         if args.ready_file:
             cmd += ["--ready-file", args.ready_file]
         procs.append(subprocess.Popen(cmd))
+    # Failure detection: losing a shard loses its column slice, so the group cannot continue.
+    # The first rank that exits abnormally takes the whole group down (exact pids of our own children only);
+    # clients see their pending request fail and recover from the last checkpoint with a fresh group.
     rc = 0
-    for p in procs:
-        rc = p.wait() or rc
+    alive = list(procs)
+    while alive:
+        time.sleep(0.2)
+        for p in list(alive):
+            code = p.poll()
+            if code is None:
+                continue
+            alive.remove(p)
+            if code != 0:
+                rc = rc or code
+                log.error("shard process %d exited with code %s: stopping the group", p.pid, code)
+                for q in alive:
+                    q.terminate()
+                deadline = time.time() + 10
+                for q in alive:
+                    try:
+                        q.wait(timeout=max(0.1, deadline - time.time()))
+                    except Exception:
+                        q.kill()
+                alive = []
+                break
     sys.exit(rc)
 
 

@@ -3,6 +3,7 @@ single-process oracle (BASELINE.json config 1: vocab 10k, dim 64,
 neg 5, window 5 on CPU world_size=2 over Gloo)."""
 import os
 import socket
+import time
 
 import numpy as np
 import pytest
@@ -213,3 +214,63 @@ def test_checkpoint_resume_reproduces_uninterrupted_run(tmp_path):
                                  EngineOptions(batch_size=100))
     assert torch.equal(eng.syn0, ref.syn0) and torch.equal(eng.syn1, ref.syn1)
     assert rep.steps == 24 - 15
+
+
+def test_killed_shard_aborts_cleanly_and_training_resumes(tmp_path):
+    """Fault injection: kill one shard process of an integrated group in the middle of `fit`.
+    The client's request must FAIL (not hang), the group must stop, and a fresh group must be able to resume
+    from the last checkpoint and finish the run."""
+    import threading
+    import psutil
+    from glint_word2vec_b200.models import checkpoint
+    from glint_word2vec_b200.parallel import cluster
+    v, d = 1500, 32
+    counts = zipf_counts(v, 10 ** 5)
+    toks = zipf_tokens(build_alias(counts.astype(np.float64)), 60000, seed=8)
+    corpus = EncodedCorpus(toks, np.arange(0, 60001, 40, dtype=np.int64))
+    cfg = SGNSConfig(v, d, seed=4)
+    opts = {"batch_size": 100, "step_tokens": 500}
+    ckdir = str(tmp_path / "ck")
+    train_opts = {"checkpoint_dir": ckdir, "checkpoint_every_steps": 5}
+
+    h = cluster.spawn_integrated(2, "cpu", opts)
+    launcher = h._procs[0]
+    try:
+        h.create(cfg, opts, counts)
+        err = {}
+
+        def run():
+            try:
+                h.fit(corpus, 0.05, 3, 60000, train_opts=train_opts)
+            except Exception as e:          # ServerError / EOFError / ConnectionError: the request failed
+                err["e"] = e
+        th = threading.Thread(target=run)
+        th.start()
+        t0 = time.time()
+        while checkpoint.latest(ckdir) is None:                       # training is under way
+            assert time.time() - t0 < 120 and th.is_alive()
+            time.sleep(0.05)
+        ranks = [c for c in psutil.Process(launcher.pid).children() if "--rank" in c.cmdline()]
+        victim = [c for c in ranks if c.cmdline()[c.cmdline().index("--rank") + 1] == "1"][0]
+        victim.kill()                                                 # exact pid of the shard we started
+        th.join(timeout=120)
+        assert not th.is_alive(), "fit() hung after a shard died"
+        assert "e" in err, "fit() must fail when a shard dies"
+        assert launcher.wait(timeout=60) != 0                         # the launcher stopped the whole group
+    finally:
+        if launcher.poll() is None:
+            launcher.kill()
+    st_path = checkpoint.latest(ckdir)
+    assert st_path is not None
+    # recovery: fresh group, resume from the last checkpoint
+    h2 = cluster.spawn_integrated(2, "cpu", opts)
+    try:
+        h2.create(cfg, opts, counts)
+        rep = h2.fit(corpus, 0.05, 3, 60000, train_opts=dict(train_opts, resume=True))
+        from glint_word2vec_b200.data.corpus import iter_steps
+        total_steps = 3 * sum(1 for _ in iter_steps(corpus, 500))
+        assert 0 < rep["steps"] < total_steps                          # only the remainder was trained
+        vecs = h2.pull(np.arange(10))
+        assert np.isfinite(vecs).all()
+    finally:
+        h2.terminate()

@@ -80,16 +80,19 @@ def _worker(rank, world, port, d, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,d,nvls,serve_fused", [(2, 128, 0, 1), (2, 100, 0, 1), (2, 128, 1, 0), (4, 256, 0, 1),
-                                                      (8, 512, 0, 1), (8, 512, 1, 1)])
-def test_fused_multi_matches_oracle(world, d, nvls, serve_fused, tmp_path, monkeypatch):
+@pytest.mark.parametrize("world,d,nvls,serve_fused,debug", [(2, 128, 0, 1, 0), (2, 100, 0, 1, 0), (2, 128, 1, 0, 0),
+                                                            (2, 64, 0, 1, 16), (4, 256, 0, 1, 0), (8, 512, 0, 1, 0),
+                                                            (8, 512, 1, 1, 16)])
+def test_fused_multi_matches_oracle(world, d, nvls, serve_fused, debug, tmp_path, monkeypatch):
     """nvls=1: the batch push uses multimem.st on the NVLS multicast mapping when the driver grants one
     (falls back to per-peer stores otherwise).  serve_fused=0: serving ops as kernel + NCCL collective
-    instead of the in-kernel peer pushes."""
+    instead of the in-kernel peer pushes.  debug=16: ranks are de-synchronised by random in-kernel delays."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     monkeypatch.setenv("GW2V_NVLS", str(nvls))
     monkeypatch.setenv("GW2V_SERVE_FUSED", str(serve_fused))
+    # debug=16: random per-warp delays before every push (flag/slot protocol stress test, SURVEY.md 5.2)
+    monkeypatch.setenv("GW2V_DEBUG", str(debug))
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), d, str(tmp_path)), nprocs=world, join=True)
     r = torch.load(os.path.join(tmp_path, "result.pt"))
