@@ -193,17 +193,19 @@ def main():
     barrier()
     launches0 = ops.launches
     sampler.start()
+    t_host0 = time.perf_counter()
     ev0.record()
     for s in range(W, n_steps):
         stats_keep.append(run_step(s).clone())
     ev1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K          # host time to QUEUE one step (diagnostic)
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ops.launches - launches0
     pairs = float(sum(float(x[0]) for x in stats_keep))
     value = pairs / (ms * 1e-3)
     result.update({"value": value, "ms_per_step": ms / K, "gpu_launches": launches if args.impl == "fused" else 0,
-                   "pairs_per_step": pairs / K})
+                   "pairs_per_step": pairs / K, "host_enqueue_ms_per_step": host_enqueue_ms})
 
     # ------------------------------------------------------------------ end to end through the public API
     if n_e2e:

@@ -100,6 +100,11 @@ class CudaShardOps:
         self._props = torch.cuda.get_device_properties(self.dev)
         self._copy_stream = None
         self._stage = []
+        # optional cap on queued steps (0 = unlimited).  Measured on 4 GPUs: pacing the host does not reduce the
+        # in-kernel waits (0.51-0.58 ms free-running vs 0.55-0.68 ms with a cap of 2), so the default is off.
+        self._max_inflight = int(os.environ.get("GW2V_MAX_INFLIGHT", "0"))
+        self._step_events = [None] * max(1, self._max_inflight)
+        self._step_i = 0
         # world > 1: serving collectives are fused into the kernels (ops/serving.py); GW2V_SERVE_FUSED=0 falls
         # back to kernel + NCCL collective (kept for A/B measurements)
         self.serve_fused = engine.comm.world > 1 and os.environ.get("GW2V_SERVE_FUSED", "1") != "0"
@@ -276,7 +281,25 @@ class CudaShardOps:
 
     def train_step_device(self, tok_dev: torch.Tensor, sid_dev: torch.Tensor, t: int, raw_pos0: int,
                           iteration: int, alpha: float) -> torch.Tensor:
-        """One step on tokens that already live on the device (int32 tensors of length >= t)."""
+        """One step on tokens that already live on the device (int32 tensors of length >= t).
+
+        With ``GW2V_MAX_INFLIGHT=m > 0`` at most m steps are queued on the device (the host waits for the end of
+        step s - m before queueing step s); the host needs ~35 us to queue a step, so the device never starves."""
+        m = self._max_inflight
+        if m > 0:
+            ring = self._step_events
+            i = self._step_i % m
+            if ring[i] is not None:
+                ring[i].synchronize()
+            else:
+                ring[i] = torch.cuda.Event()
+        stats = self._train_step_device_impl(tok_dev, sid_dev, t, raw_pos0, iteration, alpha)
+        if m > 0:
+            self._step_events[self._step_i % m].record(torch.cuda.current_stream(self.dev))
+            self._step_i += 1
+        return stats
+
+    def _train_step_device_impl(self, tok_dev, sid_dev, t, raw_pos0, iteration, alpha) -> torch.Tensor:
         cfg = self.cfg
         e = self.e
         self._ensure_capacity(t)
