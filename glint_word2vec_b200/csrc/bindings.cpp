@@ -106,19 +106,19 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                      int64_t grid, int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs,
                      std::vector<int64_t> flag_ptrs, c10::optional<Tensor> warp_seq, c10::optional<Tensor> error_flag,
                      c10::optional<Tensor> timing, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs,
-                     Tensor desc, Tensor ticket, Tensor chain, int64_t epoch, int64_t xbuf_mc, int64_t flags_mc,
+                     Tensor desc, Tensor tile_ws, int64_t xbuf_mc,
                      c10::optional<Tensor> exp_table) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
     CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
     CHECK_DT(alias, torch::kInt32); CHECK_DT(stats, torch::kFloat32); CHECK_DT(cinfo, torch::kInt32);
     CHECK_DT(pair_off, torch::kInt32); CHECK_DT(n_pairs, torch::kInt32); CHECK_DT(desc, torch::kInt32);
-    CHECK_DT(ticket, torch::kInt32); CHECK_DT(chain, torch::kInt64);
+    CHECK_DT(tile_ws, torch::kInt32);
     TORCH_CHECK(gw2v::sgns_pairs_supported((int)syn0.size(1), (int)window, (int)negatives), "sgns_pairs: unsupported shape");
     const int pd = gw2v::pairgen_desc_ints((int)negatives);
     TORCH_CHECK(cinfo.numel() >= max_tokens && pair_off.numel() >= max_tokens, "pairgen workspaces too small");
     TORCH_CHECK(desc.numel() >= max_tokens * 2 * window * pd, "descriptor buffer too small");
-    TORCH_CHECK(chain.numel() >= gw2v::pairgen_max_blocks((int)max_tokens), "chain buffer too small");
+    TORCH_CHECK(tile_ws.numel() >= gw2v::pairgen_max_blocks((int)max_tokens), "tile workspace too small");
     TORCH_CHECK(max_tokens <= gw2v::pairgen_max_tokens(), "step too large for the pair generator (max ", gw2v::pairgen_max_tokens(), " tokens)");
     c10::cuda::CUDAGuard guard(syn0.device());
     gw2v::SgnsParams p{};
@@ -149,9 +149,7 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                          p.iteration, p.pos0, p.window, p.window_mode, p.negatives,
                          reinterpret_cast<uint32_t*>(cinfo.data_ptr<int>()), pair_off.data_ptr<int>(),
                          n_pairs.data_ptr<int>(), desc.data_ptr<int>(),
-                         reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()),
-                         reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch,
-                         stats.data_ptr<float>(), cur_stream());
+                         tile_ws.data_ptr<int>(), stats.data_ptr<float>(), cur_stream());
     if (world > 1) {
         TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
         TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
@@ -163,7 +161,6 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
         p.error_flag = error_flag->data_ptr<int>();
         p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
         p.xbuf_mc = reinterpret_cast<float*>(xbuf_mc);
-        p.flags_mc = reinterpret_cast<uint32_t*>(flags_mc);
         gw2v::launch_sgns_pairs_multi(p, desc.data_ptr<int>(), n_pairs.data_ptr<int>(), pd, (int)grid,
                                       reinterpret_cast<uint32_t*>(warp_seq->data_ptr<int>()), cur_stream());
     } else {
@@ -180,10 +177,10 @@ int64_t sgns_multi_max_grid(int64_t K, int64_t window, int64_t negatives, int64_
 
 void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thresh, int64_t seed,
                        int64_t iteration, int64_t raw_pos0, Tensor tok_out, Tensor sid_out, Tensor count_out,
-                       Tensor ticket, Tensor chain, int64_t epoch) {
+                       Tensor tile_ws) {
     CHECK_CUDA(tok_in); CHECK_DT(tok_in, torch::kInt32); CHECK_DT(sid_in, torch::kInt32);
-    CHECK_DT(keep_thresh, torch::kInt32); CHECK_DT(chain, torch::kInt64); CHECK_DT(ticket, torch::kInt32);
-    TORCH_CHECK(chain.numel() >= gw2v::subsample_max_blocks((int)T), "chain buffer too small");
+    CHECK_DT(keep_thresh, torch::kInt32); CHECK_DT(tile_ws, torch::kInt32);
+    TORCH_CHECK(tile_ws.numel() >= gw2v::subsample_max_blocks((int)T), "tile workspace too small");
     TORCH_CHECK(T <= gw2v::subsample_max_tokens(), "step too large for the sub-sampling scan (max ",
                 gw2v::subsample_max_tokens(), " tokens)");
     TORCH_CHECK(tok_out.numel() >= T && sid_out.numel() >= T, "output buffers too small");
@@ -193,8 +190,7 @@ void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thre
         reinterpret_cast<const uint32_t*>(keep_thresh.data_ptr<int>()),
         (uint32_t)((uint64_t)seed & 0xFFFFFFFFull), (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull),
         (uint32_t)iteration, (unsigned long long)raw_pos0, tok_out.data_ptr<int>(), sid_out.data_ptr<int>(),
-        count_out.data_ptr<int>(), reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()),
-        reinterpret_cast<unsigned long long*>(chain.data_ptr<int64_t>()), (uint32_t)epoch, cur_stream());
+        count_out.data_ptr<int>(), tile_ws.data_ptr<int>(), cur_stream());
     check_launch("subsample_compact");
 }
 

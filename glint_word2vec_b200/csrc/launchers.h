@@ -9,7 +9,7 @@ namespace gw2v {
 void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const uint32_t* keep_thresh,
                               uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration,
                               unsigned long long raw_pos0, int* tok_out, int* sid_out, int* count_out,
-                              unsigned int* ticket, unsigned long long* chain, uint32_t epoch,
+                              int* tile_ws,
                               cudaStream_t stream);
 int subsample_max_blocks(int max_tokens);
 int subsample_max_tokens();
@@ -25,7 +25,7 @@ int pairgen_max_tokens();
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
                     int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, unsigned int* ticket, unsigned long long* chain, uint32_t epoch, float* stats,
+                    int* desc, int* tile_ws, float* stats,
                     cudaStream_t stream);   // stats (4 floats, may be null) is zeroed by the scan kernel
 
 // infer_kernels.cu

@@ -163,15 +163,14 @@ int pairgen_max_tokens() { return 1024 * PC_TILE; }
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
                     int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
-                    float* stats, cudaStream_t stream) {
+                    int* desc, int* tile_ws, float* stats, cudaStream_t stream) {
     if (max_tokens <= 0) {
         cudaMemsetAsync(n_pairs, 0, sizeof(int), stream);
         if (stats) cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream);
         return;
     }
     const int grid = (max_tokens + PC_TILE - 1) / PC_TILE;          // <= 1024 (checked by the binding)
-    int* tile_sum = reinterpret_cast<int*>(chain);                   // reuse the workspace: >= grid ints
+    int* tile_sum = tile_ws;                                         // >= grid ints
     pair_count_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration, pos0,
                                                        window, window_mode, cinfo, pair_off, tile_sum);
     pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, n_pairs, stats);

@@ -121,11 +121,11 @@ subsample_scatter_kernel(const int* __restrict__ tok_in, const int* __restrict__
 void launch_subsample_compact(const int* tok_in, const int* sid_in, int T, const uint32_t* keep_thresh,
                               uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration,
                               unsigned long long raw_pos0, int* tok_out, int* sid_out, int* count_out,
-                              unsigned int* /*ticket*/, unsigned long long* chain, uint32_t /*epoch*/,
+                              int* tile_ws,
                               cudaStream_t stream) {
     if (T <= 0) { cudaMemsetAsync(count_out, 0, sizeof(int), stream); return; }
     const int grid = (T + SC_TILE - 1) / SC_TILE;                  // <= 1024 tiles (512 k tokens per step)
-    int* tile_sum = reinterpret_cast<int*>(chain);
+    int* tile_sum = tile_ws;                                       // >= grid ints
     subsample_count_kernel<<<grid, SC_THREADS, 0, stream>>>(tok_in, T, keep_thresh, seed_lo, seed_hi, iteration,
                                                             raw_pos0, tile_sum);
     subsample_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, count_out);

@@ -239,7 +239,6 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
 
     const size_t slot_stride = PK_XSTRIDE;                                       // floats per (slot, source)
     const size_t warp_x_base = (size_t)gwarp * PK_NSLOT * S * slot_stride;
-    uint32_t* my_flags = p.flags[rank] + (size_t)gwarp * S;
     const uint32_t seq0 = warp_seq[gwarp];
     float loss = 0.f, maxdot = 0.f;
     unsigned long long wait_ns = 0;

@@ -33,7 +33,6 @@ struct SgnsParams {
     float* xbuf[MAX_WORLD];      // peer-mapped exchange buffers, xbuf[r] lives on rank r
     uint32_t* flags[MAX_WORLD];  // peer-mapped flag arrays [grid * world]
     float* xbuf_mc;              // multicast alias of xbuf (NVLS), or null
-    uint32_t* flags_mc;          // multicast alias of the flag arrays, or null
     uint32_t* cta_seq;           // [grid] running tile sequence number per CTA (local)
     int* error_flag;             // set by the spin watchdog
     unsigned long long* timing;  // optional [grid*2]: accumulated wait ns, tiles (exposed all-reduce time)

@@ -80,8 +80,6 @@ class CudaShardOps:
         self.keep_dev: Optional[torch.Tensor] = None
         self.subsample_active = True
         self._cap = 0
-        self._epoch = 0
-        self._pg_epoch = 0
         self._stats_ring = None
         self._stats_i = 0
         self._xchg = None
@@ -149,8 +147,7 @@ class CudaShardOps:
         self.tok_c = torch.empty(cap, dtype=torch.int32, device=d)
         self.sid_c = torch.empty(cap, dtype=torch.int32, device=d)
         self.count = torch.zeros(1, dtype=torch.int32, device=d)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=d)
-        self.chain = torch.zeros(int(_C.subsample_max_blocks(cap)) + 1, dtype=torch.int64, device=d)
+        self.sc_tiles = torch.zeros(int(_C.subsample_max_blocks(cap)) + 1, dtype=torch.int32, device=d)
         self._stats_ring = torch.zeros(256, 4, dtype=torch.float32, device=d)
         self._count_val = -1
         # pair-generation workspaces (pairgen.cu)
@@ -160,8 +157,7 @@ class CudaShardOps:
         self.pg_off = torch.empty(cap, dtype=torch.int32, device=d)
         self.pg_npairs = torch.zeros(1, dtype=torch.int32, device=d)
         self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd, dtype=torch.int32, device=d)
-        self.pg_ticket = torch.zeros(1, dtype=torch.int32, device=d)
-        self.pg_chain = torch.zeros(int(_C.pairgen_max_blocks(cap)) + 1, dtype=torch.int64, device=d)
+        self.pg_tiles = torch.zeros(int(_C.pairgen_max_blocks(cap)) + 1, dtype=torch.int32, device=d)
         self._cap = cap
 
     # ------------------------------------------------------------------ cross-shard exchange
@@ -222,7 +218,6 @@ class CudaShardOps:
             "mc": buf.multicast_ptr,
             # NVLS multicast push (multimem.st) is opt-in: GW2V_NVLS=1 and a multicast mapping granted by the driver
             "mc_x": buf.multicast_ptr if (buf.multicast_ptr and os.environ.get("GW2V_NVLS", "0") == "1") else 0,
-            "mc_f": (buf.multicast_ptr + xbytes) if (buf.multicast_ptr and os.environ.get("GW2V_NVLS", "0") == "1") else 0,
             "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
             "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
         }
@@ -306,10 +301,8 @@ class CudaShardOps:
         if self.world > 1 and self._xchg is None:
             self._setup_exchange()
         if self.subsample_active:
-            self._epoch += 1
             _C.subsample_compact(tok_dev, sid_dev, t, self.keep_dev, int(cfg.seed), int(iteration),
-                                 int(raw_pos0), self.tok_c, self.sid_c, self.count, self.ticket, self.chain,
-                                 self._epoch)
+                                 int(raw_pos0), self.tok_c, self.sid_c, self.count, self.sc_tiles)
             self.launches += 3            # count, tile scan, scatter
             self._count_val = -1
             tok, sid = self.tok_c, self.sid_c
@@ -327,13 +320,12 @@ class CudaShardOps:
         wm = WINDOW_MODES[cfg.window_mode]
         if self.world > 1 and self._xchg["variant"] == 3:
             x = self._xchg
-            self._pg_epoch += 1
             _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
                                int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank,
                                x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
-                               self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_ticket,
-                               self.pg_chain, self._pg_epoch, x["mc_x"], x["mc_f"], self.exp_table)
+                               self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_tiles,
+                               x["mc_x"], self.exp_table)
             self.launches += 3            # + the training kernel counted below
         elif self.world > 1:
             x = self._xchg
@@ -346,12 +338,11 @@ class CudaShardOps:
             if not hasattr(self, "_grid1"):
                 self._variant, self._grid1 = self._pick_single_kernel()
             if self._variant == 3:
-                self._pg_epoch += 1
-                _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                    _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
                                    int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                    float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
                                    None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
-                                   self.pg_ticket, self.pg_chain, self._pg_epoch, 0, 0, self.exp_table)
+                                   self.pg_tiles, 0, self.exp_table)
                 self.launches += 4            # pair_count, pair_tile_scan, pair_fill, sgns_pairs
                 return stats
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),

@@ -68,12 +68,11 @@ def test_subsample_compact_matches_numpy():
         tok_out = torch.zeros(t, dtype=torch.int32, device=dev)
         sid_out = torch.zeros(t, dtype=torch.int32, device=dev)
         count = torch.zeros(1, dtype=torch.int32, device=dev)
-        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        chain = torch.zeros(int(C.subsample_max_blocks(t)) + 1, dtype=torch.int64, device=dev)
-        for epoch in (1, 2):      # second launch re-uses ticket/chain
+        tiles = torch.zeros(int(C.subsample_max_blocks(t)) + 1, dtype=torch.int32, device=dev)
+        for _ in (1, 2):          # second launch re-uses the tile workspace
             C.subsample_compact(torch.from_numpy(tokens).to(dev), torch.from_numpy(sid).to(dev), t,
                                 torch.from_numpy(keep.view(np.int32).copy()).to(dev), 99, 2, 1000,
-                                tok_out, sid_out, count, ticket, chain, epoch)
+                                tok_out, sid_out, count, tiles)
             n = int(count.item())
             assert n == int(mask.sum())
             assert np.array_equal(tok_out[:n].cpu().numpy(), tokens[mask])
