@@ -261,18 +261,56 @@ Tensor scores_rows(Tensor syn0, Tensor qs) {
     return out;
 }
 
+// candidate capacity per query of the threshold filter; beyond it the exact chunk-wise path takes over
+constexpr int64_t TOPK_FILTER_CAP = 8192;
+
+// Select the candidates of the top-k of `nvalid` rows.  Fast path: threshold from an evenly spread sample + one
+// streaming filter pass (serve_fused.cu); if any query overflows the candidate buffer (adversarial data), every
+// chunk is ranked exactly instead.  Returns {cand_v [Q, ncand], cand_i [Q, ncand]}.
+std::vector<Tensor> topk_candidates(const float* slab, int nsrc, int64_t Q, int64_t vown, int64_t nvalid,
+                                    const float* norms_owned, int64_t row_base, int64_t k,
+                                    const torch::TensorOptions& fopt) {
+    auto iopt = fopt.dtype(torch::kInt64);
+    const char* env = getenv("GW2V_TOPK_FILTER");
+    const bool use_filter = !(env && env[0] == '0') && k <= 64 && nvalid > TOPK_FILTER_CAP;
+    if (use_filter) {
+        int ns = gw2v::topk_sample_chunks(nvalid);
+        auto cand_s_v = torch::empty({Q, std::max<int64_t>(1, ns * k)}, fopt);
+        auto cand_s_i = torch::empty({Q, std::max<int64_t>(1, ns * k)}, iopt);
+        auto tau_v = torch::empty({Q, k}, fopt);
+        auto tau_i = torch::empty({Q, k}, iopt);
+        auto cand_v = torch::empty({Q, TOPK_FILTER_CAP}, fopt);
+        auto cand_i = torch::empty({Q, TOPK_FILTER_CAP}, iopt);
+        auto counts = torch::empty({Q}, fopt.dtype(torch::kInt32));
+        gw2v::launch_topk_select(slab, nsrc, (int)Q, vown, nvalid, norms_owned, row_base, (int)k,
+                                 cand_s_v.data_ptr<float>(), reinterpret_cast<long long*>(cand_s_i.data_ptr<int64_t>()),
+                                 tau_v.data_ptr<float>(), reinterpret_cast<long long*>(tau_i.data_ptr<int64_t>()),
+                                 cand_v.data_ptr<float>(), reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()),
+                                 counts.data_ptr<int>(), (int)TOPK_FILTER_CAP, cur_stream());
+        check_launch("topk_select");
+        if (counts.max().item<int>() <= TOPK_FILTER_CAP) return {cand_v, cand_i};      // one small D2H sync
+    }
+    int nchunks = gw2v::topk_owned_num_chunks(nvalid);
+    auto cand_v = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, fopt);
+    auto cand_i = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, iopt);
+    gw2v::launch_topk_owned_stage1(slab, nsrc, (int)Q, vown, nvalid, norms_owned, row_base, (int)k,
+                                   cand_v.data_ptr<float>(), reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()),
+                                   cur_stream());
+    check_launch("topk_stage1");
+    if (nchunks == 0) { cand_v.fill_(-3.0e38f); cand_i.fill_(-1); }
+    return {cand_v, cand_i};
+}
+
 std::vector<Tensor> cosine_topk(Tensor scores, Tensor norms, int64_t k) {
     CHECK_CUDA(scores); CHECK_CUDA(norms); CHECK_CONTIG(scores); CHECK_CONTIG(norms);
     c10::cuda::CUDAGuard guard(scores.device());
     int64_t Q = scores.size(0), V = scores.size(1);
-    int nchunks = gw2v::topk_num_chunks(V);
-    auto cand_v = torch::empty({Q, (int64_t)nchunks * k}, scores.options());
-    auto cand_i = torch::empty({Q, (int64_t)nchunks * k}, scores.options().dtype(torch::kInt64));
+    auto cand = topk_candidates(scores.data_ptr<float>(), 1, Q, V, V, norms.data_ptr<float>(), 0, k, scores.options());
     auto out_v = torch::empty({Q, k}, scores.options());
     auto out_i = torch::empty({Q, k}, scores.options().dtype(torch::kInt64));
-    gw2v::launch_cosine_topk(scores.data_ptr<float>(), norms.data_ptr<float>(), V, (int)Q, (int)k,
-                             cand_v.data_ptr<float>(), reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()), out_v.data_ptr<float>(),
-                             reinterpret_cast<long long*>(out_i.data_ptr<int64_t>()), cur_stream());
+    gw2v::launch_topk_merge(cand[0].data_ptr<float>(), reinterpret_cast<const long long*>(cand[1].data_ptr<int64_t>()),
+                            (int)cand[0].size(1), (int)Q, (int)k, out_v.data_ptr<float>(),
+                            reinterpret_cast<long long*>(out_i.data_ptr<int64_t>()), cur_stream());
     check_launch("cosine_topk");
     return {out_i, out_v};
 }
@@ -423,17 +461,14 @@ void serve_topk_owned_push(ServeCtx& c, Tensor slab_local, int64_t nsrc, int64_t
                            std::vector<int64_t> candi_ptrs) {
     CHECK_CUDA(slab_local); CHECK_CUDA(norms_owned);
     c10::cuda::CUDAGuard guard(slab_local.device());
+    auto cand = topk_candidates(slab_local.data_ptr<float>(), (int)nsrc, Q, vown, nvalid, norms_owned.data_ptr<float>(),
+                                row_base, k, slab_local.options());
     gw2v::ServeSync s = c.next();
-    int nchunks = gw2v::topk_owned_num_chunks(nvalid);
-    auto cand_v = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, slab_local.options());
-    auto cand_i = torch::empty({Q, std::max<int64_t>(1, (int64_t)nchunks * k)}, slab_local.options().dtype(torch::kInt64));
     gw2v::PeerIdx pi{};
     TORCH_CHECK((int64_t)candi_ptrs.size() == c.world, "need one candidate-index pointer per rank");
     for (int64_t r = 0; r < c.world; ++r) pi.p[r] = reinterpret_cast<long long*>(candi_ptrs[r]);
-    gw2v::launch_topk_owned_push(slab_local.data_ptr<float>(), (int)nsrc, (int)Q, vown, nvalid,
-                                 norms_owned.data_ptr<float>(), row_base, (int)k, cand_v.data_ptr<float>(),
-                                 reinterpret_cast<long long*>(cand_i.data_ptr<int64_t>()), peer_ptrs(c, candv_ptrs), pi,
-                                 s, cur_stream());
+    gw2v::launch_topk_merge_push(cand[0].data_ptr<float>(), reinterpret_cast<const long long*>(cand[1].data_ptr<int64_t>()),
+                                 (int)cand[0].size(1), (int)Q, (int)k, peer_ptrs(c, candv_ptrs), pi, s, cur_stream());
     check_launch("topk_owned_push");
     c.wait(s);
 }

@@ -4,8 +4,8 @@
 //   row_sqnorm         norms() partial (sum of squares) MLLIB:486
 //   scores_rows        multiply(): syn0_shard . q_shard for a batch of queries (CUDA-core path;
 //                      the tcgen05 path lives in nn_tc.cu)
-//   cosine_topk        fused  score/norm (zero norm -> 0) + per-chunk top-k, then merge
-//                      (replaces the driver-side loop + BoundedPriorityQueue, MLLIB:600-617)
+//   topk_merge         final k of a candidate list (candidate selection: serve_fused.cu); together they
+//                      replace the driver-side loop + BoundedPriorityQueue of MLLIB:600-617
 #include "common.cuh"
 #include "launchers.h"
 #include <float.h>
@@ -170,34 +170,8 @@ __device__ __forceinline__ void block_argmax(const float* vals, int n, float& be
     __syncthreads();
 }
 
-// stage 1: per (query, chunk): cos = score / norm (0 if norm == 0); emit the chunk's top-k
-__global__ void __launch_bounds__(TK_THREADS)
-cosine_topk_stage1_kernel(const float* __restrict__ scores, const float* __restrict__ norms, long long V, int k,
-                          float* __restrict__ cand_v, long long* __restrict__ cand_i, int nchunks) {
-    __shared__ float vals[TK_CHUNK];
-    __shared__ float red_v[TK_THREADS / 32];
-    __shared__ int red_i[TK_THREADS / 32];
-    const int q = blockIdx.y, chunk = blockIdx.x;
-    const long long base = (long long)chunk * TK_CHUNK;
-    const int n = (int)min((long long)TK_CHUNK, V - base);
-    for (int i = threadIdx.x; i < n; i += TK_THREADS) {
-        float nr = __ldg(norms + base + i);
-        float sc = __ldg(scores + (size_t)q * V + base + i);
-        vals[i] = nr > 0.f ? sc / nr : 0.f;
-    }
-    __syncthreads();
-    for (int j = 0; j < k; ++j) {
-        float bv; int bi;
-        block_argmax(vals, n, bv, bi, red_v, red_i);
-        if (threadIdx.x == 0) {
-            size_t o = ((size_t)q * nchunks + chunk) * k + j;
-            cand_v[o] = (bi >= 0) ? bv : -FLT_MAX;
-            cand_i[o] = (bi >= 0) ? base + bi : -1;
-            if (bi >= 0) vals[bi] = -FLT_MAX;
-        }
-        __syncthreads();
-    }
-}
+// (stage 1 - candidate selection by threshold filter or per-chunk arg-max - lives in serve_fused.cu and serves
+// both the single-shard and the column-shard path)
 
 // stage 2: one block per query merges nchunks*k candidates
 __global__ void __launch_bounds__(TK_THREADS)
@@ -224,17 +198,6 @@ void launch_topk_merge(float* cand_v, const long long* cand_i, int ncand, int Q,
                        long long* out_i, cudaStream_t s) {
     if (Q <= 0) return;
     topk_merge_kernel<<<Q, TK_THREADS, 0, s>>>(cand_v, cand_i, ncand, k, out_v, out_i);
-}
-
-int topk_num_chunks(long long V) { return (int)((V + TK_CHUNK - 1) / TK_CHUNK); }
-
-void launch_cosine_topk(const float* scores, const float* norms, long long V, int Q, int k, float* cand_v,
-                        long long* cand_i, float* out_v, long long* out_i, cudaStream_t s) {
-    if (V <= 0 || Q <= 0) return;
-    int nchunks = topk_num_chunks(V);
-    dim3 grid(nchunks, Q);
-    cosine_topk_stage1_kernel<<<grid, TK_THREADS, 0, s>>>(scores, norms, V, k, cand_v, cand_i, nchunks);
-    topk_merge_kernel<<<Q, TK_THREADS, 0, s>>>(cand_v, cand_i, nchunks * k, k, out_v, out_i);
 }
 
 }  // namespace gw2v

@@ -35,9 +35,6 @@ void launch_segment_mean_rows(const float* syn0, const long long* rows, const lo
 void launch_row_sqnorm(const float* syn0, long long V, int K, float* out, int sms, cudaStream_t s);
 void launch_scores_rows(const float* syn0, long long V, int K, const float* qs, int Q, float* out, int sms,
                         cudaStream_t s);
-int topk_num_chunks(long long V);
-void launch_cosine_topk(const float* scores, const float* norms, long long V, int Q, int k, float* cand_v,
-                        long long* cand_i, float* out_v, long long* out_i, cudaStream_t s);
 void launch_topk_merge(float* cand_v, const long long* cand_i, int ncand, int Q, int k, float* out_v,
                        long long* out_i, cudaStream_t s);
 

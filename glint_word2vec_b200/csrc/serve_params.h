@@ -34,6 +34,16 @@ int topk_owned_num_chunks(long long nvalid);
 void launch_topk_owned_push(const float* slab_local, int nsrc, int Q, long long vown, long long nvalid,
                             const float* norms_owned, long long row_base, int k, float* cand_v, long long* cand_i,
                             const PeerPtrs& out_v, const PeerIdx& out_i, const ServeSync& s, cudaStream_t st);
+int topk_sample_chunks(long long nvalid);
+void launch_topk_select(const float* slab_local, int nsrc, int Q, long long vown, long long nvalid,
+                        const float* norms_owned, long long row_base, int k, float* cand_s_v, long long* cand_s_i,
+                        float* tau_v, long long* tau_i, float* cand_f_v, long long* cand_f_i, int* counts, int cap,
+                        cudaStream_t st);
+void launch_topk_merge_push(float* cand_v, const long long* cand_i, int ncand, int Q, int k, const PeerPtrs& out_v,
+                            const PeerIdx& out_i, const ServeSync& s, cudaStream_t st);
+void launch_topk_owned_stage1(const float* slab_local, int nsrc, int Q, long long vown, long long nvalid,
+                              const float* norms_owned, long long row_base, int k, float* cand_v, long long* cand_i,
+                              cudaStream_t st);
 void launch_push_block(const float* src, long long n, const PeerPtrs& dst, const ServeSync& s, cudaStream_t st);
 // nn_tc.cu: tcgen05 score GEMM whose epilogue stores each tile into the owner rank's slab (reduce-scatter)
 int launch_scores_tc_push(const float* syn0, long long V, int K, const float* qpad, int Q, const PeerPtrs& slab,

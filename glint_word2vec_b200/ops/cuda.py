@@ -338,7 +338,7 @@ class CudaShardOps:
             if not hasattr(self, "_grid1"):
                 self._variant, self._grid1 = self._pick_single_kernel()
             if self._variant == 3:
-                    _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
                                    int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                    float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
                                    None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,

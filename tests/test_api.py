@@ -248,3 +248,16 @@ def test_fit_accepts_plain_iterables_and_encoded():
     m2 = est.fitEncoded(toks, np.arange(0, 151, 5), np.array([60, 60, 30]))
     assert m2.numWords == 3 and m2._words[2] == "w2" and m2.transformWord("w1").shape == (8,)
     m2.stop()
+
+
+def test_every_module_compiles():
+    """GPU-only modules are never imported by the CPU tier; a syntax error there must still fail here."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "glint_word2vec_b200", "**", "*.py"), recursive=True)
+    files += [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py", "benchmarks/bench_nn.py",
+                                              "baseline/nccl_sgns.py", "scripts/run_integration.py")]
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True)

@@ -256,6 +256,36 @@ def test_inference_kernels_match_torch():
     assert (idx16 == ri16).float().mean() > 0.95
 
 
+def test_topk_threshold_filter_is_exact(monkeypatch):
+    """Candidate selection by sampled threshold + one filter pass must return exactly what the per-chunk
+    arg-max path returns - including on data that overflows the candidate buffer (falls back)."""
+    dev = _dev()
+    C = _C()
+    g = torch.Generator().manual_seed(3)
+    v, q, k = 300000, 7, 10
+    scores = torch.randn(q, v, generator=g).to(dev)
+    norms = (torch.rand(v, generator=g) + 0.5).to(dev)
+    norms[123] = 0.0
+    cos = torch.where(norms > 0, scores / norms, torch.zeros_like(scores))
+    want_v, want_i = torch.topk(cos, k, dim=1)
+    monkeypatch.setenv("GW2V_TOPK_FILTER", "1")
+    i1, v1 = C.cosine_topk(scores.clone(), norms, k)
+    monkeypatch.setenv("GW2V_TOPK_FILTER", "0")
+    i0, v0 = C.cosine_topk(scores.clone(), norms, k)
+    assert torch.equal(v1, want_v) and torch.equal(v0, want_v)
+    assert torch.equal(i1, want_i) and torch.equal(i0, want_i)
+    # adversarial: every row ties -> every element passes the threshold -> buffer overflow -> exact fallback
+    monkeypatch.setenv("GW2V_TOPK_FILTER", "1")
+    flat = torch.ones(q, v, device=dev)
+    it, vt = C.cosine_topk(flat, torch.ones(v, device=dev), k)
+    assert torch.equal(vt, torch.ones(q, k, device=dev))
+    assert int(it.min()) >= 0 and all(len(set(r.tolist())) == k for r in it.cpu())
+    # rows sorted by score: the sample must still bound the true k-th best
+    ramp = torch.arange(v, dtype=torch.float32, device=dev).repeat(2, 1)
+    ir, vr = C.cosine_topk(ramp, torch.ones(v, device=dev), k)
+    assert ir[0].tolist() == list(range(v - 1, v - 1 - k, -1))
+
+
 def test_fit_on_gpu_golden(corpus_sentences):
     """Scenario 1/10/12 of the reference spec on the device path (SPEC:83-106,290-352)."""
     _dev()
