@@ -29,7 +29,7 @@ log = logging.getLogger("glint_word2vec_b200")
 JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
 _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "concurrency", "deterministic", "kernel",
-                "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "device")
+                "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")
 
 
 def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:
@@ -57,7 +57,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
     """PS bootstrap (C9): separate cluster if a host is given, SPMD if this
     process is one rank of a torchrun job, in-process for one shard, else spawn
     an integrated shard-server group."""
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "device")}
+    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")}
     if host:
         h = _cluster.connect_separate(host)
         return h.create(cfg, engine_opts, counts)
@@ -76,7 +76,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
 
 
 def open_handle_for_load(path: str, host: str, num_servers: int, opts: dict):
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "device")}
+    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")}
     if host:
         h = _cluster.connect_separate(host)
         h.load(path, engine_opts)
@@ -175,7 +175,8 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
                          negatives=self.getN(), seed=self.getSeed(),
                          window_mode=pcfg.get("window_mode", "reference"),
                          sigmoid_mode=pcfg.get("sigmoid_mode", "exact"),
-                         max_grad=float(pcfg.get("max_grad", 0.0)))
+                         max_grad=float(pcfg.get("max_grad", 0.0)),
+                         neg_sharing=pcfg.get("neg_sharing", "pair"))
         opts = engine_options_from_params(self)
         handle = open_handle_for_fit(cfg, vocab.counts, self.getParameterServerHost(),
                                      self.getNumParameterServers(), opts)

@@ -106,7 +106,7 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                      int64_t grid, int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs,
                      std::vector<int64_t> flag_ptrs, c10::optional<Tensor> warp_seq, c10::optional<Tensor> error_flag,
                      c10::optional<Tensor> timing, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs,
-                     Tensor desc, Tensor tile_ws, int64_t xbuf_mc,
+                     Tensor desc, Tensor tile_ws, int64_t xbuf_mc, int64_t share_centre,
                      c10::optional<Tensor> exp_table) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
@@ -146,7 +146,7 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     p.debug = (int)debug;
     p.world = (int)world; p.rank = (int)rank;
     gw2v::launch_pairgen(p.tokens, p.sent_id, p.n_tokens, (int)max_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi,
-                         p.iteration, p.pos0, p.window, p.window_mode, p.negatives,
+                         p.iteration, p.pos0, p.window, p.window_mode, p.negatives, (int)share_centre,
                          reinterpret_cast<uint32_t*>(cinfo.data_ptr<int>()), pair_off.data_ptr<int>(),
                          n_pairs.data_ptr<int>(), desc.data_ptr<int>(),
                          tile_ws.data_ptr<int>(), stats.data_ptr<float>(), cur_stream());

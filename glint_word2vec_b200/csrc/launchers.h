@@ -24,8 +24,8 @@ int pairgen_desc_ints(int negatives);
 int pairgen_max_tokens();
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
-                    int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, int* tile_ws, float* stats,
+                    int window, int window_mode, int negatives, int share_centre, uint32_t* cinfo, int* pair_off,
+                    int* n_pairs, int* desc, int* tile_ws, float* stats,
                     cudaStream_t stream);   // stats (4 floats, may be null) is zeroed by the scan kernel
 
 // infer_kernels.cu

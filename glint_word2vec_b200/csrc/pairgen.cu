@@ -114,7 +114,7 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
                                  const int* __restrict__ tile_prefix,
                                  const int2* __restrict__ alias, int vocab, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t iteration, unsigned long long pos0, int window, int negatives, int slots,
-                                 int pd, int* __restrict__ desc) {
+                                 int pd, int share_centre, int* __restrict__ desc) {
     const int T = *n_tokens;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i = gid / slots;
@@ -132,7 +132,7 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     e[1] = ctok;
     const int ncalls = (negatives + 1) >> 1;
     const uint32_t sw = stream_word(STREAM_NEG, iteration);
-    const int slot = off + window;
+    const int slot = share_centre ? 0 : off + window;     // neg_sharing="centre": one draw per centre
     // all Philox calls first, then all alias-table reads in flight together (they are independent random
     // 8-byte reads into an 80 MB table), then the selects - the serial version cost 28 us per step
     uint32_t idx[8], sel[8];
@@ -162,8 +162,8 @@ int pairgen_max_tokens() { return 1024 * PC_TILE; }
 // per-tile counts + local offsets -> scan of the tile sums -> descriptor fill.
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,
-                    int window, int window_mode, int negatives, uint32_t* cinfo, int* pair_off, int* n_pairs,
-                    int* desc, int* tile_ws, float* stats, cudaStream_t stream) {
+                    int window, int window_mode, int negatives, int share_centre, uint32_t* cinfo, int* pair_off,
+                    int* n_pairs, int* desc, int* tile_ws, float* stats, cudaStream_t stream) {
     if (max_tokens <= 0) {
         cudaMemsetAsync(n_pairs, 0, sizeof(int), stream);
         if (stats) cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream);
@@ -179,7 +179,7 @@ void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, 
     pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, tile_sum,
                                                                          alias, vocab, seed_lo, seed_hi, iteration,
                                                                          pos0, window, negatives, slots,
-                                                                         pairgen_desc_ints(negatives), desc);
+                                                                         pairgen_desc_ints(negatives), share_centre, desc);
 }
 
 }  // namespace gw2v

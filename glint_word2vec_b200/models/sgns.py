@@ -39,8 +39,14 @@ class SGNSConfig:
     window_mode: str = "reference"      # "reference" (Q2) | "word2vec_c"
     sigmoid_mode: str = "exact"         # "exact" | "table" (MLLIB:281-302 parity)
     max_grad: float = 0.0               # optional |g| clip (0 = off)
+    # "pair": n private negatives per (centre, context) pair - the reference's behaviour (one seed per request,
+    # MLLIB:420-421).  "centre": the n negatives are drawn once per centre and shared by all of its pairs
+    # (pWord2Vec-style sharing): same expected gradient, the negative rows of a centre stay hot in L2.
+    neg_sharing: str = "pair"
 
     def __post_init__(self):
+        if self.neg_sharing not in ("pair", "centre"):
+            raise ValueError(f"unknown neg_sharing {self.neg_sharing!r}")
         if self.window_mode not in ("reference", "word2vec_c"):
             raise ValueError(f"unknown window_mode {self.window_mode!r}")
         if self.sigmoid_mode not in ("exact", "table"):
@@ -114,6 +120,8 @@ def draw_negatives(cfg: SGNSConfig, alias: AliasTable, pos: np.ndarray, slot: np
     p = pos.shape[0]
     n = cfg.negatives
     out = np.empty((p, n), dtype=np.int32)
+    if cfg.neg_sharing == "centre":
+        slot = np.zeros_like(slot)                      # every pair of a centre draws the same negatives
     for c in range(cfg.neg_calls):
         sub = (slot.astype(np.uint64) * np.uint64(cfg.neg_calls) + np.uint64(c))
         r0, r1, r2, r3 = philox.rand4(cfg.seed, philox.STREAM_NEG, pos, sub, iteration)

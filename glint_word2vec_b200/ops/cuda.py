@@ -91,6 +91,7 @@ class CudaShardOps:
         if self._loopback > 1:
             self.debug |= 8
         # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
+        self._share_centre = 1 if engine.cfg.neg_sharing == "centre" else 0
         self.exp_table = None
         if engine.cfg.sigmoid_mode == "table":
             from ..models.sgns import _exp_table
@@ -174,6 +175,8 @@ class CudaShardOps:
             want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
         variant = 3 if (want == "pairs" and pairs_ok) else (
             2 if (want == "group" and group_ok) else (1 if (want == "pipe" and pipe_ok) else 0))
+        if variant != 3 and self._share_centre:
+            raise RuntimeError('neg_sharing="centre" is implemented by the pairs kernel only')
         if variant == 3:
             grid = int(_C.sgns_pairs_grid(self.K, dev_index, True))
             warps, nslot, slot_floats = [int(x) for x in _C.sgns_pairs_multi_geometry()]
@@ -325,7 +328,7 @@ class CudaShardOps:
                                float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank,
                                x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
                                self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_tiles,
-                               x["mc_x"], self.exp_table)
+                               x["mc_x"], self._share_centre, self.exp_table)
             self.launches += 3            # + the training kernel counted below
         elif self.world > 1:
             x = self._xchg
@@ -342,7 +345,7 @@ class CudaShardOps:
                                    int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                    float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
                                    None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
-                                   self.pg_tiles, 0, self.exp_table)
+                                   self.pg_tiles, 0, self._share_centre, self.exp_table)
                 self.launches += 4            # pair_count, pair_tile_scan, pair_fill, sgns_pairs
                 return stats
             _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
@@ -386,6 +389,8 @@ class CudaShardOps:
             want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
         if want == "pairs" and pairs_ok:
             return 3, int(_C.sgns_pairs_grid(self.K, dev_index, False))
+        if self._share_centre:
+            raise RuntimeError('neg_sharing="centre" is implemented by the pairs kernel only')
         if want == "group" and group_ok:
             return 2, int(_C.sgns_group_grid(self.K, dev_index))
         if want == "pipe" and pipe_ok:

@@ -159,3 +159,29 @@ def test_sigmoid_table_mode_close_to_exact():
 def test_synthetic_vocab_is_lazy():
     v = vocab_from_counts(np.arange(10, 0, -1))
     assert v.size == 10 and v.words[3] == "w3" and v.index["w7"] == 7 and "w11" not in v.index
+
+
+def test_neg_sharing_centre_shares_negatives_per_centre():
+    """neg_sharing="centre": one draw of n negatives per centre position, reused by all of its pairs;
+    "pair" (reference behaviour): private negatives per pair."""
+    from glint_word2vec_b200.data.sampler import build_alias, zipf_counts
+    from glint_word2vec_b200.models.sgns import SGNSConfig
+    v = 5000
+    alias = build_alias(zipf_counts(v, 10 ** 6).astype(np.float64))
+    rng = np.random.default_rng(0)
+    tokens = rng.integers(0, v, size=400).astype(np.int32)
+    sid = (np.arange(400) // 50).astype(np.int32)
+    for mode in ("pair", "centre"):
+        cfg = SGNSConfig(v, 16, 5, 5, seed=9, neg_sharing=mode)
+        ci, cj, slot = sgns.enumerate_pairs(cfg, tokens, sid, 777, 0)
+        negs = sgns.draw_negatives(cfg, alias, np.uint64(777) + ci.astype(np.uint64), slot, 0)
+        same = 0
+        total = 0
+        for a in range(1, len(ci)):
+            if ci[a] == ci[a - 1]:
+                total += 1
+                same += int(np.array_equal(negs[a], negs[a - 1]))
+        assert total > 100
+        assert same == (total if mode == "centre" else 0) or (mode == "pair" and same < 3)
+    with pytest.raises(ValueError):
+        SGNSConfig(v, 16, neg_sharing="batch")

@@ -165,6 +165,33 @@ def test_sgns_step_sigmoid_table_mode(variant, monkeypatch):
     assert float((e0 - r0).norm() / r0.norm()) > 1e-4
 
 
+def test_sgns_step_neg_sharing_centre_matches_oracle():
+    """neg_sharing="centre" (negatives drawn once per centre, shared by its pairs) against the oracle in the
+    same mode; the pair count and the negatives are bit-identical, the updates agree to Hogwild tolerance."""
+    dev = _dev()
+    v, d = 200000, 64
+    cfg = SGNSConfig(v, d, 5, 5, seed=7, neg_sharing="centre")
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng.init_weights()
+    eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
+    g = torch.Generator().manual_seed(0)
+    syn1 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    syn0 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    eng.syn0, eng.syn1 = syn0.to(dev), syn1.to(dev)
+    t = 3000
+    tokens = np.random.default_rng(1).choice(v, size=t, replace=False).astype(np.int32)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0.clone(), syn1.clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 4242, 0, 0.002)
+    stats = eng.train_step(tokens, sid, 4242, 0, 0.002).cpu()
+    assert int(stats[0]) == st.pairs
+    assert abs(float(stats[1]) - st.loss) / st.loss < 2e-3
+    d0, r0 = eng.syn0.cpu() - syn0, ref0 - syn0
+    d1, r1 = eng.syn1.cpu() - syn1, ref1 - syn1
+    assert (d0 - r0).norm() / r0.norm() < 2e-2
+    assert (d1 - r1).norm() / r1.norm() < 3e-2       # shared negatives: the same row takes several updates per centre
+
+
 def test_sgns_step_hot_rows_hogwild_close():
     """Dense collisions (tiny vocabulary): updates race by design; the result
     must still be close to the summed mini-batch oracle and finite."""
