@@ -128,13 +128,12 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     const int rank = __popc(mask & ((1u << q) - 1u));
     int* e = desc + (size_t)(__ldg(tile_prefix + (int)(i / PC_TILE)) + __ldg(pair_off + i) + rank) * pd;
     const int ctok = __ldg(tokens + i + off);
-    e[0] = __ldg(tokens + i);
-    e[1] = ctok;
+    const int wtok = __ldg(tokens + i);
     const int ncalls = (negatives + 1) >> 1;
     const uint32_t sw = stream_word(STREAM_NEG, iteration);
     const int slot = share_centre ? 0 : off + window;     // neg_sharing="centre": one draw per centre
     // all Philox calls first, then all alias-table reads in flight together (they are independent random
-    // 8-byte reads into an 80 MB table), then the selects - the serial version cost 28 us per step
+    // 8-byte reads into an 80 MB table), then the selects; the descriptor leaves as 16-byte stores
     uint32_t idx[8], sel[8];
     int2 ent[8];
 #pragma unroll
@@ -148,9 +147,16 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         if (j < negatives) ent[j] = __ldg(alias + idx[j]);
+    int w[12];
+    w[0] = wtok; w[1] = ctok;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        if (j < negatives) e[2 + j] = (sel[j] < (uint32_t)ent[j].x) ? (int)idx[j] : ent[j].y;
+        w[2 + j] = (j < negatives) ? ((sel[j] < (uint32_t)ent[j].x) ? (int)idx[j] : ent[j].y) : 0;
+    w[10] = w[11] = 0;
+    int4* e4 = reinterpret_cast<int4*>(e);                 // pd is a multiple of 4 ints: 16-byte aligned
+    e4[0] = make_int4(w[0], w[1], w[2], w[3]);
+    e4[1] = make_int4(w[4], w[5], w[6], w[7]);
+    if (pd > 8) e4[2] = make_int4(w[8], w[9], w[10], w[11]);
 }
 
 int pairgen_max_blocks(int max_tokens) { return (max_tokens + PC_TILE - 1) / PC_TILE + 1; }
@@ -174,7 +180,9 @@ void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, 
     pair_count_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration, pos0,
                                                        window, window_mode, cinfo, pair_off, tile_sum);
     pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum, grid, n_pairs, stats);
-    const int slots = 2 * window + 1;
+    // offset slots a centre can use: reference window (Q2) spans [-b, b-1] with b <= window-1 -> 2(window-1) slots
+    int slots = (window_mode == 0) ? 2 * (window - 1) : 2 * window + 1;
+    if (slots < 1) slots = 1;
     const long long total = (long long)max_tokens * slots;
     pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, tile_sum,
                                                                          alias, vocab, seed_lo, seed_hi, iteration,
