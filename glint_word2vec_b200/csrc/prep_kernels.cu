@@ -4,7 +4,7 @@
 //                       scatter), sentence ids ride along.
 //   zipf_stream       : synthetic Zipf token stream from the alias table.
 //   init_syn0         : syn0 ~ U(-0.5,0.5)/d as a pure function of (row, col).
-// Windowing (K7) and negative sampling (K5) are fused into sgns_fused.
+// Windowing (K7) and negative sampling (K5): pairgen.cu.
 #include "common.cuh"
 #include "launchers.h"
 

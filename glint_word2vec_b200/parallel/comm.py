@@ -2,7 +2,7 @@
 
 One process per GPU, ``torch.distributed`` for rendezvous and cold-path
 collectives (NCCL on GPUs, Gloo for the CPU plumbing configuration of
-BASELINE.json).  The HOT path (partial-dot all-reduce inside ``sgns_fused``)
+BASELINE.json).  The HOT path (partial-dot all-reduce inside ``csrc/sgns_pairs.cu``)
 does not go through this module on GPUs: it uses symmetric-memory peer
 pointers from ``parallel.symm`` inside the kernel.
 
