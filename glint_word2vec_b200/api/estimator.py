@@ -28,7 +28,7 @@ log = logging.getLogger("glint_word2vec_b200")
 
 JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
-_ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "concurrency", "deterministic", "kernel",
+_ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "kernel",
                 "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")
 
 

@@ -46,10 +46,13 @@ class EngineOptions:
     subsample_ratio: float = 1e-6
     subsample_mode: str = "reference"   # "reference" (Q1: the reference's sub-sampling is inert) | "word2vec"
     max_hot_updates: int = 256          # auto step size: expected stale summed updates on the hottest row per step
-    transport: str = "auto"         # auto | p2p | nvls | nccl | gloo
-    concurrency: int = 0            # mini-batches in flight per step (0 = auto)
-    deterministic: bool = False     # two-phase kernels (all dots, then all updates)
-    kernel: str = "auto"            # auto | fused | twophase
+    # How partial dots travel between column shards on GPUs:
+    #   "auto"/"p2p": in-kernel st.global pushes into the peers' symmetric memory (the product)
+    #   "nvls":       same kernel, one multimem.st per chunk on the NVLS multicast mapping
+    #   "nccl"/"gloo": the un-fused Glint-style path (dotprod -> library all-reduce -> adjust) with the reference's
+    #                  mini-batch semantics on any device; slow, kept for A/B runs and as the CPU path
+    transport: str = "auto"
+    kernel: str = "auto"            # training kernel: auto | pairs | group | pipe | v1 (csrc/; env GW2V_*_KERNEL wins)
     store_syn1: bool = True         # keep syn1neg in saves (retrainable)
 
     @classmethod
@@ -57,6 +60,18 @@ class EngineOptions:
         d = dict(d or {})
         known = {k: d[k] for k in list(d) if k in cls.__dataclass_fields__}
         return cls(**known)
+
+    def __post_init__(self):
+        if self.transport not in ("auto", "p2p", "nvls", "nccl", "gloo"):
+            raise ValueError(f"unknown transport {self.transport!r}")
+        if self.kernel not in ("auto", "pairs", "group", "pipe", "v1"):
+            raise ValueError(f"unknown kernel {self.kernel!r}")
+
+
+def _host_i32(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        x = x.cpu().numpy()
+    return np.asarray(x, dtype=np.int32)
 
 
 class _ReadyHandle:
@@ -93,6 +108,11 @@ class ShardEngine:
     @property
     def is_cuda(self) -> bool:
         return self.device.type == "cuda"
+
+    @property
+    def unfused(self) -> bool:
+        """True when the step runs as dotprod -> library all-reduce -> adjust (CPU, or transport nccl/gloo)."""
+        return (not self.is_cuda) or self.opts.transport in ("nccl", "gloo")
 
     @property
     def vocab_size(self) -> int:
@@ -160,10 +180,9 @@ class ShardEngine:
         if self.alias is None:
             raise RuntimeError("set_noise() must be called before training")
         self._norms = None
-        if self.is_cuda:
+        if self.is_cuda and not self.unfused:
             return self._cuda.train_step(tokens, sent_id, raw_pos0, iteration, alpha)
-        return self._train_step_cpu(np.asarray(tokens, dtype=np.int32), np.asarray(sent_id, dtype=np.int32),
-                                    raw_pos0, iteration, alpha)
+        return self._train_step_cpu(_host_i32(tokens), _host_i32(sent_id), raw_pos0, iteration, alpha)
 
     def train_step_async(self, tokens, sent_id, raw_pos0: int, iteration: int, alpha: float):
         """``train_step`` whose statistics are read back asynchronously: returns a handle with
@@ -172,10 +191,9 @@ class ShardEngine:
         if self.alias is None:
             raise RuntimeError("set_noise() must be called before training")
         self._norms = None
-        if self.is_cuda:
+        if self.is_cuda and not self.unfused:
             return self._cuda.train_step_async(tokens, sent_id, raw_pos0, iteration, alpha)
-        return _ReadyHandle(self._train_step_cpu(np.asarray(tokens, dtype=np.int32),
-                                                 np.asarray(sent_id, dtype=np.int32), raw_pos0, iteration, alpha))
+        return _ReadyHandle(self._train_step_cpu(_host_i32(tokens), _host_i32(sent_id), raw_pos0, iteration, alpha))
 
     def _train_step_cpu(self, tokens, sent_id, raw_pos0, iteration, alpha):
         cfg = self.cfg
@@ -223,9 +241,9 @@ class ShardEngine:
         pos = np.uint64(pos0) + ci.astype(np.uint64)
         neg = sgns.draw_negatives(cfg, self.alias, pos, slot, iteration)
         tok = tokens.astype(np.int64)
-        w = torch.from_numpy(tok[ci])
-        c = torch.from_numpy(tok[cj])
-        ng = torch.from_numpy(neg.astype(np.int64))
+        w = torch.from_numpy(tok[ci]).to(self.device)
+        c = torch.from_numpy(tok[cj]).to(self.device)
+        ng = torch.from_numpy(neg.astype(np.int64)).to(self.device)
         f = self.partial_dots(w, c, ng)
         f = self.comm.all_reduce_sum(f)                   # the Glint client-side aggregation
         neg_mask = (ng != c[:, None]).to(torch.float32)

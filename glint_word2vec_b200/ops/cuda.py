@@ -167,7 +167,7 @@ class CudaShardOps:
         from ..parallel.symm import alloc_symmetric
         cfg = self.cfg
         dev_index = self.dev.index or 0
-        want = os.environ.get("GW2V_MULTI_KERNEL", "auto")
+        want = os.environ.get("GW2V_MULTI_KERNEL", self.e.opts.kernel)
         pipe_ok = bool(_C.sgns_pipe_multi_supported(self.K, cfg.window, cfg.negatives))
         group_ok = bool(_C.sgns_group_multi_supported(self.K, cfg.window, cfg.negatives))
         pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))
@@ -220,11 +220,16 @@ class CudaShardOps:
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
             "mc": buf.multicast_ptr,
             # NVLS multicast push (multimem.st) is opt-in: GW2V_NVLS=1 and a multicast mapping granted by the driver
-            "mc_x": buf.multicast_ptr if (buf.multicast_ptr and os.environ.get("GW2V_NVLS", "0") == "1") else 0,
+            "mc_x": buf.multicast_ptr if (buf.multicast_ptr and self._want_nvls()) else 0,
             "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
             "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
         }
         self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
+
+    def _want_nvls(self) -> bool:
+        """multimem.st push: transport="nvls" (or GW2V_NVLS=1) and a multicast mapping granted by the driver."""
+        env = os.environ.get("GW2V_NVLS")
+        return env == "1" if env is not None else self.e.opts.transport == "nvls"
 
     # ------------------------------------------------------------------ training
     def stage_tokens(self, tokens, sent_id):
@@ -379,7 +384,7 @@ class CudaShardOps:
         """single-shard kernel variant: 2 = lane-group register path, 1 = TMA pipeline, 0 = v1."""
         cfg = self.cfg
         dev_index = self.dev.index or 0
-        want = os.environ.get("GW2V_SINGLE_KERNEL", "auto")
+        want = os.environ.get("GW2V_SINGLE_KERNEL", self.e.opts.kernel)
         group_ok = bool(_C.sgns_group_supported(self.K, cfg.window, cfg.negatives))
         pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
         pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))

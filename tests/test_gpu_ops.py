@@ -192,6 +192,35 @@ def test_sgns_step_neg_sharing_centre_matches_oracle():
     assert (d1 - r1).norm() / r1.norm() < 3e-2       # shared negatives: the same row takes several updates per centre
 
 
+def test_unfused_transport_on_gpu_has_minibatch_semantics():
+    """transport="nccl": dotprod -> (library) all-reduce -> adjust with torch ops on the device - the reference's
+    exact mini-batch semantics (all dots of a mini-batch from pre-update rows), so it matches the oracle to fp32
+    rounding, unlike the Hogwild kernels."""
+    dev = _dev()
+    v, d = 20000, 48
+    cfg = SGNSConfig(v, d, 5, 5, seed=7)
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", transport="nccl",
+                                                             batch_size=4000))
+    assert eng.unfused
+    eng.init_weights()
+    eng.set_noise(zipf_counts(v, 10 ** 6, 0.8))
+    g = torch.Generator().manual_seed(0)
+    syn1 = torch.randn(v, d, generator=g) * 0.1
+    syn0 = torch.randn(v, d, generator=g) * 0.1
+    eng.syn0, eng.syn1 = syn0.to(dev), syn1.to(dev)
+    t = 4000
+    tokens = np.random.default_rng(1).integers(0, v, size=t).astype(np.int32)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0.clone(), syn1.clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 5, 0, 0.025)
+    stats = torch.as_tensor(eng.train_step(tokens, sid, 5, 0, 0.025)).cpu()
+    assert int(stats[0]) == st.pairs
+    assert torch.allclose(eng.syn0.cpu(), ref0, atol=2e-6)
+    assert torch.allclose(eng.syn1.cpu(), ref1, atol=2e-6)
+    with pytest.raises(ValueError):
+        EngineOptions(transport="carrier-pigeon")
+
+
 def test_sgns_step_hot_rows_hogwild_close():
     """Dense collisions (tiny vocabulary): updates race by design; the result
     must still be close to the summed mini-batch oracle and finite."""
