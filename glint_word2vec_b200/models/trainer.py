@@ -98,12 +98,12 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
             rep.steps += 1
             if words_prev + words_it - last_log > log_every_words or len(pending) >= 64:
                 last_log = words_prev + words_it
-                _drain(pending, rep, alpha, words_prev + words_it, mf)
+                _drain(pending, rep, alpha, words_prev + words_it, mf, engine, t0)
             if checkpoint_fn is not None:
                 checkpoint_fn(k, si + 1)
         rep.iterations += 1
         rep.words += words_it
-    _drain(pending, rep, alpha, rep.words, mf)
+    _drain(pending, rep, alpha, rep.words, mf, engine, t0)
     if engine.is_cuda:
         torch.cuda.synchronize(engine.device)
     rep.seconds = time.time() - t0
@@ -113,7 +113,15 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
     return rep
 
 
-def _drain(pending, rep: TrainReport, alpha, words, mf):
+def _exposed_wait_ns(engine) -> Optional[int]:
+    ops = getattr(engine, "_cuda", None) if engine is not None else None
+    timing = getattr(ops, "timing", None)
+    if timing is None:
+        return None
+    return int(timing[0].item())
+
+
+def _drain(pending, rep: TrainReport, alpha, words, mf, engine=None, t0=None):
     if not pending:
         return
     vals = [p.result() if hasattr(p, "result") else p for p in pending]      # async step handles
@@ -131,6 +139,12 @@ def _drain(pending, rep: TrainReport, alpha, words, mf):
     rep.max_abs_dot = max(rep.max_abs_dot, maxdot)
     rec = {"words": int(words), "alpha": float(alpha), "pairs": pairs,
            "loss_per_pair": (loss / pairs) if pairs else None, "max_abs_dot": maxdot}
+    if t0 is not None:                                   # throughput next to the loss probe
+        rec["elapsed_s"] = time.time() - t0
+        rec["pairs_per_sec"] = rep.pairs / rec["elapsed_s"] if rec["elapsed_s"] > 0 else None
+    wait = _exposed_wait_ns(engine)
+    if wait is not None:                                 # in-kernel time spent polling for the peers' partial dots
+        rec["exposed_allreduce_wait_ns_total"] = wait
     rep.history.append(rec)
     # same probe the reference logs every 10k words: wordCount, alpha, a dot product (MLLIB:411-412)
     log.info("wordCount = %d, alpha = %.6g, loss/pair = %s, max|f| = %.4g", words, alpha,
