@@ -9,8 +9,7 @@ from __future__ import annotations
 
 import logging
 import os
-import warnings
-from typing import Iterable, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

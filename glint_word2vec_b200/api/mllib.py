@@ -8,7 +8,7 @@ OOV, ``getVectors`` as a map, ``save(path)``/``load(path[, host[, config]])``).
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple, Union
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 

@@ -10,7 +10,7 @@ sentence boundaries as a per-token sentence id so windows never cross them
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Iterable, Iterator, List, Sequence, Tuple
+from typing import Iterable, Iterator, List, Sequence
 
 import numpy as np
 

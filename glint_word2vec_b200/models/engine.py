@@ -23,9 +23,8 @@ reference (Glint) op  here
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
-from typing import Dict, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -33,7 +32,6 @@ import torch
 from ..data.sampler import AliasTable, keep_thresholds, unigram_alias
 from ..parallel.comm import Comm
 from ..parallel.sharding import ColumnShard, make_shard
-from ..utils import philox
 from . import sgns
 from .sgns import SGNSConfig
 

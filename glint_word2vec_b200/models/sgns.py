@@ -16,7 +16,7 @@ oracle, the CPU engine and the CUDA kernels draw identical windows/negatives.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass, asdict
 from typing import Optional, Tuple
 
 import numpy as np

@@ -14,8 +14,6 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ..utils import philox
-
 try:
     from .. import _C                      # built by glint_word2vec_b200/build_ext.py
 except ImportError as e:                  # pragma: no cover
@@ -90,8 +88,8 @@ class CudaShardOps:
         self.debug = int(os.environ.get("GW2V_DEBUG", "0"))      # profiling-only kernel switches
         if self._loopback > 1:
             self.debug |= 8
-        # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self._share_centre = 1 if engine.cfg.neg_sharing == "centre" else 0
+        # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self.exp_table = None
         if engine.cfg.sigmoid_mode == "table":
             from ..models.sgns import _exp_table

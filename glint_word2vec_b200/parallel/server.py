@@ -29,7 +29,7 @@ import socket
 import sys
 import time
 import traceback
-from multiprocessing.connection import Client as _ConnClient, Listener
+from multiprocessing.connection import Listener
 from typing import Dict, Optional
 
 import numpy as np
@@ -37,7 +37,7 @@ import torch
 import torch.distributed as dist
 
 from ..data.corpus import EncodedCorpus
-from ..models import matrix_io, trainer
+from ..models import matrix_io
 from ..models.engine import EngineOptions, ShardEngine
 from ..models.sgns import SGNSConfig
 from .comm import Comm, TorchDistComm, init_process_group

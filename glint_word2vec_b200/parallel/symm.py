@@ -13,7 +13,7 @@ servers.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

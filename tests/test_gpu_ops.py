@@ -6,7 +6,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from glint_word2vec_b200.data.sampler import (build_alias, keep_thresholds, unigram_alias, zipf_counts,
+from glint_word2vec_b200.data.sampler import (build_alias, keep_thresholds, zipf_counts,
                                               zipf_tokens)
 from glint_word2vec_b200.models import sgns
 from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine

@@ -1,6 +1,5 @@
 """Property-based tests (hypothesis) of the host-side building blocks (unit tier)."""
 import numpy as np
-import pytest
 from hypothesis import given, settings, strategies as st
 
 from glint_word2vec_b200.data.corpus import chunk_encoded, iter_steps, java_split
