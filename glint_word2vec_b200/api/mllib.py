@@ -12,8 +12,8 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
-from .estimator import ServerSideGlintWord2Vec
-from .model import ServerSideGlintWord2VecModel
+from .estimator import ServerSideGlintWord2Vec as _MLEstimator
+from .model import ServerSideGlintWord2VecModel as _MLModel
 
 
 class MLlibServerSideGlintWord2VecModel:
@@ -21,7 +21,7 @@ class MLlibServerSideGlintWord2VecModel:
 
     formatVersion = "1.0"                          # MLLIB:488
 
-    def __init__(self, ml_model: ServerSideGlintWord2VecModel):
+    def __init__(self, ml_model: _MLModel):
         self._m = ml_model
 
     @property
@@ -31,6 +31,10 @@ class MLlibServerSideGlintWord2VecModel:
     @property
     def vectorSize(self) -> int:                   # MLLIB:473
         return self._m._vsize
+
+    @property
+    def wordList(self) -> List[str]:               # MLLIB:478-481: words ordered by row index
+        return list(self._m._words)
 
     def transform(self, word_or_words: Union[str, Iterable[str]]):
         """``transform(word)`` -> vector; ``transform(iterator)`` -> iterator of
@@ -60,10 +64,10 @@ class MLlibServerSideGlintWord2VecModel:
     @classmethod
     def load(cls, path: str, parameterServerHost: str = "", parameterServerConfig: Optional[dict] = None):
         """MLLIB:683,696,710."""
-        return cls(ServerSideGlintWord2VecModel.load(path, parameterServerHost, parameterServerConfig))
+        return cls(_MLModel.load(path, parameterServerHost, parameterServerConfig))
 
     @property
-    def ml(self) -> ServerSideGlintWord2VecModel:
+    def ml(self) -> _MLModel:
         return self._m
 
 
@@ -71,7 +75,7 @@ class MLlibServerSideGlintWord2Vec:
     """Builder-style trainer with the 15 MLlib setters (MLLIB:92-244)."""
 
     def __init__(self):
-        self._est = ServerSideGlintWord2Vec()
+        self._est = _MLEstimator()
         # MLlib defaults that differ from the ML layer: learningRate 0.01875 is the same; seed random (MLLIB:71)
         self._est.setSeed(int(np.random.SeedSequence().entropy % (2 ** 31)))
 
@@ -139,3 +143,8 @@ class MLlibServerSideGlintWord2Vec:
     def fit(self, sentences: Iterable[Sequence[str]]) -> MLlibServerSideGlintWord2VecModel:
         """``fit(RDD[Iterable[String]])`` (MLLIB:310-326)."""
         return MLlibServerSideGlintWord2VecModel(self._est.fit(sentences))
+
+
+# the MLlib layer's own class names (org.apache.spark.mllib.feature.*), MLLIB:65,460
+ServerSideGlintWord2Vec = MLlibServerSideGlintWord2Vec
+ServerSideGlintWord2VecModel = MLlibServerSideGlintWord2VecModel

@@ -250,6 +250,15 @@ def test_fit_accepts_plain_iterables_and_encoded():
     m2.stop()
 
 
+def test_mllib_names_and_word_list(small_model):
+    """The MLlib layer's own class names and `wordList` (MLLIB:65,460,478-481)."""
+    from glint_word2vec_b200.api import mllib
+    assert mllib.ServerSideGlintWord2Vec is mllib.MLlibServerSideGlintWord2Vec
+    m = mllib.ServerSideGlintWord2VecModel(small_model)
+    assert m.wordList == [w for w, _ in sorted(small_model._index.items(), key=lambda kv: kv[1])]
+    assert m.formatVersion == "1.0" and m.vectorSize == small_model.getVectorSize()
+
+
 def test_every_module_compiles():
     """GPU-only modules are never imported by the CPU tier; a syntax error there must still fail here."""
     import glob
