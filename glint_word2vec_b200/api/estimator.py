@@ -157,6 +157,19 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
         corpus = encode_corpus(sentences, vocab, self.getMaxSentenceLength())
         return self._fit_encoded(vocab, corpus)
 
+    def fitTextFile(self, path: str, tokenizer: str = "java") -> ServerSideGlintWord2VecModel:
+        """Train on a text file with one sentence per line.  Vocabulary counting and encoding run in the native
+        host library (mmap + all cores) without ever building Python token lists - the loader for corpora of
+        the reference's scale, which it reads as Spark RDD partitions (MLLIB:258-279,335-345).
+        ``tokenizer="java"`` = the spec's ``line.split(" ")``; ``"whitespace"`` = split on runs of blanks."""
+        from ..data.corpus import encode_text_file
+        from ..data.vocab import build_vocab_from_file
+        self._validate_for_fit()
+        vocab = build_vocab_from_file(path, self.getMinCount(), tokenizer)
+        log.info("vocabSize = %d, trainWordsCount = %d", vocab.size, vocab.train_words)   # MLLIB:278
+        corpus = encode_text_file(path, vocab, self.getMaxSentenceLength(), tokenizer)
+        return self._fit_encoded(vocab, corpus)
+
     def fitEncoded(self, tokens: np.ndarray, offsets: np.ndarray, counts: np.ndarray,
                    words: Optional[Sequence[str]] = None) -> ServerSideGlintWord2VecModel:
         """Train on an already index-encoded corpus (token ids must already be

@@ -6,15 +6,24 @@
 //                  Python strings have been flattened (the GIL-bound part is only the flattening).
 //  encode_corpus : words -> vocabulary indices with OOV dropped and sentences chunked at
 //                  maxSentenceLength (MLLIB:335-343).
+//  count_words_file / encode_file : the same two passes straight from a text file (one sentence per line),
+//                  mmap'ed and split over threads at line boundaries - the data-loader path for corpora
+//                  that do not fit a Python list of lists (the reference reads them as Spark RDD partitions).
 //  vose_alias    : Vose alias construction for the unigram^0.75 noise distribution (replaces the
 //                  Glint servers' 1e8-entry unigram table, ML:204-206).
 #include <pybind11/pybind11.h>
 #include <pybind11/numpy.h>
 #include <pybind11/stl.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -30,6 +39,55 @@ struct StrHash {
         uint64_t h = 1469598103934665603ull;                 // FNV-1a
         for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
         return (size_t)h;
+    }
+};
+
+// Open-addressing string map (linear probing, power-of-two capacity, load <= 0.5).  Keys are views into storage
+// that outlives the map (the mmap'ed file or an arena); std::unordered_map cost ~2x more per token here.
+struct FlatStrMap {
+    struct Slot { uint64_t hash; const char* p; uint32_t len; int64_t val; };
+    std::vector<Slot> slots;
+    size_t mask = 0, n = 0;
+    static inline const char kEmptyKey = 0;                  // non-null address for the empty string key
+
+    explicit FlatStrMap(size_t cap_pow2 = 1 << 16) : slots(cap_pow2, Slot{0, nullptr, 0, 0}), mask(cap_pow2 - 1) {}
+
+    static uint64_t hash(std::string_view s) noexcept { return StrHash{}(s) * 0x9E3779B97F4A7C15ull; }
+
+    void grow() {
+        std::vector<Slot> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, Slot{0, nullptr, 0, 0});
+        mask = slots.size() - 1;
+        for (const Slot& o : old) {
+            if (!o.p) continue;
+            size_t i = (size_t)(o.hash >> 7) & mask;
+            while (slots[i].p) i = (i + 1) & mask;
+            slots[i] = o;
+        }
+    }
+    Slot& find_or_insert(std::string_view s, uint64_t h) {
+        if ((n + 1) * 2 > slots.size()) grow();
+        size_t i = (size_t)(h >> 7) & mask;
+        while (true) {
+            Slot& sl = slots[i];
+            if (!sl.p) {
+                sl = Slot{h, s.empty() ? &kEmptyKey : s.data(), (uint32_t)s.size(), 0};
+                ++n;
+                return sl;
+            }
+            if (sl.hash == h && sl.len == s.size() && std::memcmp(sl.p, s.data(), s.size()) == 0) return sl;
+            i = (i + 1) & mask;
+        }
+    }
+    const Slot* find(std::string_view s, uint64_t h) const noexcept {
+        size_t i = (size_t)(h >> 7) & mask;
+        while (true) {
+            const Slot& sl = slots[i];
+            if (!sl.p) return nullptr;
+            if (sl.hash == h && sl.len == s.size() && std::memcmp(sl.p, s.data(), s.size()) == 0) return &sl;
+            i = (i + 1) & mask;
+        }
     }
 };
 
@@ -129,6 +187,196 @@ py::tuple encode_corpus(const py::iterable& sentences, const py::dict& index, in
     return py::make_tuple(a, o);
 }
 
+// ------------------------------------------------------------------------------------------ text files
+// Read-only mmap of a whole file.
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    explicit MappedFile(const std::string& path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); throw std::runtime_error("cannot stat " + path); }
+        size = (size_t)st.st_size;
+        if (size > 0) {
+            void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) { ::close(fd); throw std::runtime_error("cannot mmap " + path); }
+            data = static_cast<const char*>(p);
+            madvise(p, size, MADV_SEQUENTIAL);
+        }
+    }
+    ~MappedFile() {
+        if (data) munmap(const_cast<char*>(data), size);
+        if (fd >= 0) ::close(fd);
+    }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+};
+
+// [begin, end) byte ranges that start and end on line boundaries, one per thread
+std::vector<std::pair<size_t, size_t>> line_chunks(const MappedFile& f, unsigned n) {
+    std::vector<std::pair<size_t, size_t>> out;
+    size_t begin = 0;
+    for (unsigned t = 0; t < n && begin < f.size; ++t) {
+        size_t end = (t + 1 == n) ? f.size : std::max(begin, f.size * (t + 1) / n);
+        while (end < f.size && f.data[end - 1] != '\n') ++end;        // extend to the end of the line
+        if (end > begin) out.emplace_back(begin, end);
+        begin = end;
+    }
+    return out;
+}
+
+// Calls fn(token) for every token of the line [p, e) (no newline inside).
+//   java_mode: String.split(" ") of the JVM - split on every single space, keep interior empty tokens,
+//              drop trailing empty tokens; a line without any token left yields one empty token iff the
+//              line itself is empty
+//   otherwise: split on runs of spaces / tabs / CR, never yields empty tokens
+template <typename F>
+inline void for_tokens(const char* p, const char* e, bool java_mode, F&& fn) {
+    if (e > p && e[-1] == '\r') --e;
+    if (!java_mode) {
+        while (p < e) {
+            while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+            const char* b = p;
+            while (p < e && !(*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+            if (p > b) fn(std::string_view(b, (size_t)(p - b)));
+        }
+        return;
+    }
+    if (p == e) { fn(std::string_view()); return; }                    // "" -> [""]
+    const char* last = e;
+    while (last > p && last[-1] == ' ') --last;                        // trailing empties are dropped
+    if (last == p) return;                                             // only spaces -> no tokens
+    const char* b = p;
+    for (const char* q = p; q <= last; ++q) {
+        if (q == last || *q == ' ') { fn(std::string_view(b, (size_t)(q - b))); b = q + 1; }
+    }
+}
+
+template <typename F>
+inline void for_lines(const char* p, const char* e, F&& fn) {
+    while (p < e) {
+        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(e - p)));
+        const char* le = nl ? nl : e;
+        fn(p, le);
+        p = nl ? nl + 1 : e;
+    }
+}
+
+unsigned pick_threads(int64_t requested, size_t bytes) {
+    unsigned n = requested > 0 ? (unsigned)requested : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (bytes < (1u << 20)) n = 1;
+    return n;
+}
+
+// word -> count over a text file; returns (list of words, int64 counts) in unspecified order
+py::tuple count_words_file(const std::string& path, bool java_mode, int64_t num_threads) {
+    std::vector<std::pair<std::string, int64_t>> merged;
+    {
+        py::gil_scoped_release rel;
+        MappedFile f(path);
+        auto chunks = line_chunks(f, pick_threads(num_threads, f.size));
+        std::vector<FlatStrMap> maps(chunks.size());
+        auto work = [&](size_t t) {
+            auto& m = maps[t];
+            for_lines(f.data + chunks[t].first, f.data + chunks[t].second, [&](const char* b, const char* e) {
+                for_tokens(b, e, java_mode, [&](std::string_view w) { ++m.find_or_insert(w, FlatStrMap::hash(w)).val; });
+            });
+        };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < chunks.size(); ++t) th.emplace_back(work, t);
+        if (!chunks.empty()) work(0);
+        for (auto& x : th) x.join();
+        for (size_t t = 1; t < maps.size(); ++t)
+            for (const auto& sl : maps[t].slots)
+                if (sl.p) maps[0].find_or_insert(std::string_view(sl.p, sl.len), sl.hash).val += sl.val;
+        if (!maps.empty()) {
+            merged.reserve(maps[0].n);
+            for (const auto& sl : maps[0].slots)
+                if (sl.p) merged.emplace_back(std::string(sl.p, sl.len), sl.val);          // copy before munmap
+        }
+    }
+    py::list words;
+    py::array_t<int64_t> counts((py::ssize_t)merged.size());
+    int64_t* c = counts.mutable_data();
+    for (size_t i = 0; i < merged.size(); ++i) {
+        words.append(py::reinterpret_steal<py::str>(
+            PyUnicode_DecodeUTF8(merged[i].first.data(), (Py_ssize_t)merged[i].first.size(), "replace")));
+        c[i] = merged[i].second;
+    }
+    return py::make_tuple(words, counts);
+}
+
+// text file -> (tokens int32, sentence offsets int64): OOV words dropped, sentences chunked at max_len,
+// sentences without any in-vocabulary word skipped (MLLIB:335-343); `words[i]` has index i
+py::tuple encode_file(const std::string& path, const py::list& words, int64_t max_len, bool java_mode,
+                      int64_t num_threads) {
+    // vocabulary: one arena holding the UTF-8 bytes + a flat map word -> index (read-only while encoding)
+    std::string arena;
+    std::vector<std::pair<size_t, size_t>> spans;
+    spans.reserve((size_t)py::len(words));
+    for (py::handle w : words) {
+        Py_ssize_t len = 0;
+        const char* data = PyUnicode_AsUTF8AndSize(w.ptr(), &len);
+        if (!data) throw py::error_already_set();
+        spans.emplace_back(arena.size(), (size_t)len);
+        arena.append(data, (size_t)len);
+    }
+    size_t cap = 1 << 10;
+    while (cap < spans.size() * 2 + 2) cap <<= 1;
+    FlatStrMap idx(cap);
+    for (size_t i = 0; i < spans.size(); ++i) {
+        std::string_view w(arena.data() + spans[i].first, spans[i].second);
+        auto& sl = idx.find_or_insert(w, FlatStrMap::hash(w));
+        sl.val = (int64_t)i;                              // duplicates keep the last index (callers pass unique words)
+    }
+    std::vector<std::vector<int32_t>> toks;
+    std::vector<std::vector<int64_t>> lens;          // sentence (chunk) lengths per thread
+    {
+        py::gil_scoped_release rel;
+        MappedFile f(path);
+        auto chunks = line_chunks(f, pick_threads(num_threads, f.size));
+        toks.resize(chunks.size());
+        lens.resize(chunks.size());
+        auto work = [&](size_t t) {
+            auto& tk = toks[t];
+            auto& ln = lens[t];
+            for_lines(f.data + chunks[t].first, f.data + chunks[t].second, [&](const char* b, const char* e) {
+                int64_t in_chunk = 0;
+                for_tokens(b, e, java_mode, [&](std::string_view w) {
+                    const FlatStrMap::Slot* sl = idx.find(w, FlatStrMap::hash(w));
+                    if (!sl) return;
+                    if (in_chunk == max_len) { ln.push_back(in_chunk); in_chunk = 0; }
+                    tk.push_back((int32_t)sl->val);
+                    ++in_chunk;
+                });
+                if (in_chunk > 0) ln.push_back(in_chunk);
+            });
+        };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < chunks.size(); ++t) th.emplace_back(work, t);
+        if (!chunks.empty()) work(0);
+        for (auto& x : th) x.join();
+    }
+    size_t ntok = 0, nsent = 0;
+    for (auto& v : toks) ntok += v.size();
+    for (auto& v : lens) nsent += v.size();
+    py::array_t<int32_t> a((py::ssize_t)ntok);
+    py::array_t<int64_t> o((py::ssize_t)nsent + 1);
+    int32_t* ap = a.mutable_data();
+    int64_t* op = o.mutable_data();
+    size_t at = 0, os = 0;
+    int64_t run = 0;
+    op[os++] = 0;
+    for (size_t t = 0; t < toks.size(); ++t) {
+        if (!toks[t].empty()) std::memcpy(ap + at, toks[t].data(), toks[t].size() * sizeof(int32_t));
+        at += toks[t].size();
+        for (int64_t l : lens[t]) { run += l; op[os++] = run; }
+    }
+    return py::make_tuple(a, o);
+}
+
 py::tuple vose_alias(py::array_t<double, py::array::c_style | py::array::forcecast> p) {
     const int64_t v = (int64_t)p.size();
     const double* pp = p.data();
@@ -164,5 +412,8 @@ PYBIND11_MODULE(_host, m) {
     m.doc() = "glint_word2vec_b200 native host library";
     m.def("count_words", &count_words);
     m.def("encode_corpus", &encode_corpus);
+    m.def("count_words_file", &count_words_file, py::arg("path"), py::arg("java_mode") = true, py::arg("num_threads") = 0);
+    m.def("encode_file", &encode_file, py::arg("path"), py::arg("words"), py::arg("max_len"),
+          py::arg("java_mode") = true, py::arg("num_threads") = 0);
     m.def("vose_alias", &vose_alias);
 }

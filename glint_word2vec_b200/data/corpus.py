@@ -81,6 +81,32 @@ def chunk_encoded(tokens: np.ndarray, offsets: np.ndarray, max_sentence_length: 
     return EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(new_offs, np.int64))
 
 
+def iter_text_file(path: str, tokenizer: str = "java") -> Iterator[List[str]]:
+    """Sentences of a text file (one per line) as token lists; the pure-Python twin of the native loader."""
+    with open(path, encoding="utf-8", errors="replace", newline="\n") as f:
+        for line in f:
+            if line.endswith("\n"):
+                line = line[:-1]
+            if line.endswith("\r"):
+                line = line[:-1]
+            yield java_split(line) if tokenizer == "java" else line.replace("\t", " ").replace("\r", " ").split()
+
+
+def encode_text_file(path: str, vocab: Vocabulary, max_sentence_length: int = 1000, tokenizer: str = "java",
+                     use_native: bool = True, num_threads: int = 0) -> EncodedCorpus:
+    """Text file -> encoded corpus (OOV dropped, sentences chunked, MLLIB:335-343) without materialising Python
+    token lists: ``csrc/host/textproc.cpp::encode_file`` mmaps the file and encodes on all cores."""
+    if tokenizer not in ("java", "whitespace"):
+        raise ValueError(f"unknown tokenizer {tokenizer!r}")
+    if use_native:
+        from ..ops import host as _host
+        if _host.available():
+            toks, offs = _host.encode_file(path, list(vocab.words), int(max_sentence_length), tokenizer == "java",
+                                           num_threads)
+            return EncodedCorpus(toks, offs)
+    return encode_corpus(iter_text_file(path, tokenizer), vocab, max_sentence_length, use_native=False)
+
+
 @dataclass
 class StepBatch:
     """One device step: whole sentences, at most ``step_tokens`` tokens."""

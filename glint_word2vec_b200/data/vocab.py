@@ -81,6 +81,37 @@ def build_vocab(sentences: Iterable[Sequence[str]], min_count: int = 5,
     return Vocabulary(words, cn)
 
 
+def _vocab_from_counts_dict(counts, min_count: int) -> Vocabulary:
+    items = [(w, c) for w, c in counts if c >= min_count]
+    if not items:
+        raise ValueError(
+            "The vocabulary size should be > 0. You may need to check the setting of "
+            "minCount, which could be large enough to remove all your words in sentences.")
+    items.sort(key=lambda wc: (-wc[1], wc[0].encode("utf-8")))
+    words = [w for w, _ in items]
+    cn = np.fromiter((c for _, c in items), dtype=np.int64, count=len(items))
+    return Vocabulary(words, cn)
+
+
+def build_vocab_from_file(path: str, min_count: int = 5, tokenizer: str = "java", use_native: bool = True,
+                          num_threads: int = 0) -> Vocabulary:
+    """``learnVocab`` straight from a text file with one sentence per line.
+
+    ``tokenizer="java"`` splits like the reference's spec does (``line.split(" ")`` on the JVM: single spaces,
+    interior empty tokens kept, Q9); ``"whitespace"`` splits on runs of blanks.  The native path mmaps the file
+    and counts on all cores (``csrc/host/textproc.cpp::count_words_file``)."""
+    if tokenizer not in ("java", "whitespace"):
+        raise ValueError(f"unknown tokenizer {tokenizer!r}")
+    if use_native:
+        from ..ops import host as _host
+        if _host.available():
+            words, counts = _host.count_words_file(path, tokenizer == "java", num_threads)
+            return _vocab_from_counts_dict(zip(words, counts.tolist()), min_count)
+    from .corpus import iter_text_file
+    c = count_words_python(iter_text_file(path, tokenizer))
+    return _vocab_from_counts_dict(c.items(), min_count)
+
+
 def vocab_from_counts(counts: np.ndarray, words: Sequence[str] | None = None) -> Vocabulary:
     """Vocabulary for synthetic corpora: word i is ``"w<i>"`` unless given."""
     counts = np.asarray(counts, dtype=np.int64)

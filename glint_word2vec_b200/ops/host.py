@@ -48,3 +48,17 @@ def vose_alias(p: np.ndarray):
     m = _load()
     prob, alias = m.vose_alias(np.ascontiguousarray(p, dtype=np.float64))
     return np.asarray(prob), np.asarray(alias)
+
+
+def count_words_file(path: str, java_mode: bool = True, num_threads: int = 0):
+    """(words, counts int64) of a text file, one sentence per line."""
+    m = _load()
+    words, counts = m.count_words_file(str(path), bool(java_mode), int(num_threads))
+    return words, np.asarray(counts, dtype=np.int64)
+
+
+def encode_file(path: str, words, max_sentence_length: int, java_mode: bool = True, num_threads: int = 0):
+    """(tokens int32, offsets int64) of a text file against the vocabulary ``words`` (index = position)."""
+    m = _load()
+    toks, offs = m.encode_file(str(path), list(words), int(max_sentence_length), bool(java_mode), int(num_threads))
+    return np.asarray(toks, dtype=np.int32), np.asarray(offs, dtype=np.int64)

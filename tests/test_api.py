@@ -259,6 +259,26 @@ def test_mllib_names_and_word_list(small_model):
     assert m.formatVersion == "1.0" and m.vectorSize == small_model.getVectorSize()
 
 
+def test_fit_text_file_equals_fit_on_sentences(tmp_path):
+    """`fitTextFile` (native mmap loader) trains the same model as `fit` on the tokenised sentences."""
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    sentences = synthetic_capitals_corpus(seed=3)[:1500]
+    path = tmp_path / "corpus.txt"
+    path.write_text("\n".join(" ".join(s) for s in sentences), encoding="utf-8")
+    kw = dict(inputCol="sentence", outputCol="vec", vectorSize=16, minCount=2, seed=5, numParameterServers=1,
+              parameterServerConfig={"device": "cpu"})
+    m1 = ServerSideGlintWord2Vec(**kw).fitTextFile(str(path))
+    m2 = ServerSideGlintWord2Vec(**kw).fit(sentences)
+    try:
+        assert m1.numWords == m2.numWords
+        v1, v2 = m1.getVectorsMap(), m2.getVectorsMap()
+        assert v1.keys() == v2.keys()
+        assert all(np.array_equal(v1[w], v2[w]) for w in list(v1)[:50])
+    finally:
+        m1.stop()
+        m2.stop()
+
+
 def test_every_module_compiles():
     """GPU-only modules are never imported by the CPU tier; a syntax error there must still fail here."""
     import glob

@@ -185,3 +185,44 @@ def test_neg_sharing_centre_shares_negatives_per_centre():
         assert same == (total if mode == "centre" else 0) or (mode == "pair" and same < 3)
     with pytest.raises(ValueError):
         SGNSConfig(v, 16, neg_sharing="batch")
+
+
+@pytest.mark.parametrize("tokenizer", ["java", "whitespace"])
+def test_text_file_loader_matches_in_memory_path(tmp_path, tokenizer):
+    """Native mmap/multi-thread file loader == pure-Python file reader == in-memory sentence path,
+    including empty lines, leading/trailing/double spaces, CRLF and a missing final newline."""
+    from glint_word2vec_b200.data.corpus import encode_corpus, encode_text_file, iter_text_file
+    from glint_word2vec_b200.data.vocab import build_vocab, build_vocab_from_file
+    from glint_word2vec_b200.ops import host
+    rng = np.random.default_rng(0)
+    words = [f"w{i}" for i in range(300)] + ["ö", "日本"]
+    lines = []
+    for i in range(60000):
+        n = int(rng.integers(0, 12))
+        toks = [words[int(rng.zipf(1.5)) % len(words)] for _ in range(n)]
+        sep = "  " if i % 97 == 0 else " "
+        line = sep.join(toks)
+        if i % 53 == 0:
+            line = " " + line
+        if i % 59 == 0:
+            line = line + "  "
+        lines.append(line)
+    lines[10] = ""
+    lines[11] = "   "
+    body = "\n".join(lines[:30000]) + "\r\n" + "\n".join(lines[30000:])        # > 1 MiB -> several threads
+    path = tmp_path / "corpus.txt"
+    path.write_bytes(body.encode("utf-8"))
+    sentences = list(iter_text_file(str(path), tokenizer))
+    assert len(sentences) == 60000
+    ref_vocab = build_vocab(sentences, 3, use_native=False)
+    ref_corpus = encode_corpus(sentences, ref_vocab, 7, use_native=False)
+    for native in ([True, False] if host.available() else [False]):
+        v = build_vocab_from_file(str(path), 3, tokenizer, use_native=native)
+        assert v.words == ref_vocab.words and np.array_equal(v.counts, ref_vocab.counts)
+        c = encode_text_file(str(path), v, 7, tokenizer, use_native=native)
+        assert np.array_equal(c.tokens, ref_corpus.tokens)
+        assert np.array_equal(c.offsets, ref_corpus.offsets)
+    if tokenizer == "java":
+        assert "" in ref_vocab.index                       # Q9: the empty token is a word
+    else:
+        assert "" not in ref_vocab.index
