@@ -194,6 +194,7 @@ def main():
     for s in range(W):
         run_step(s)
     barrier()
+    wait0 = int(ops.timing[0].item()) if (world > 1 and ops.timing is not None) else 0
     launches0 = ops.launches
     sampler.start()
     t_host0 = time.perf_counter()
@@ -204,6 +205,13 @@ def main():
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K          # host time to QUEUE one step (diagnostic)
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
+    if world > 1 and ops.timing is not None and ops._xchg is not None:
+        # in-kernel %globaltimer time spent polling for the peers' partial dots, timed region only:
+        # mean over the exchanging warps, per step (a mini-batch of the reference = 50 centres of this step)
+        warps = ops._xchg["grid"] * 8
+        wait_us = (int(ops.timing[0].item()) - wait0) / 1e3 / max(1, warps) / K
+        result["exposed_allreduce_us_per_step"] = max_over_ranks(wait_us)
+        result["exposed_allreduce_fraction_of_step"] = result["exposed_allreduce_us_per_step"] / (ms / K * 1e3)
     launches = ops.launches - launches0
     pairs = float(sum(float(x[0]) for x in stats_keep))
     value = pairs / (ms * 1e-3)
