@@ -28,7 +28,8 @@ log = logging.getLogger("glint_word2vec_b200")
 JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
 _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "kernel",
-                "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")
+                "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
+                "tile_negatives", "device")
 
 
 def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:
@@ -56,7 +57,8 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
     """PS bootstrap (C9): separate cluster if a host is given, SPMD if this
     process is one rank of a torchrun job, in-process for one shard, else spawn
     an integrated shard-server group."""
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")}
+    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
+                                                        "tile_negatives", "device")}
     if host:
         h = _cluster.connect_separate(host)
         return h.create(cfg, engine_opts, counts)
@@ -75,7 +77,8 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
 
 
 def open_handle_for_load(path: str, host: str, num_servers: int, opts: dict):
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "device")}
+    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
+                                                        "tile_negatives", "device")}
     if host:
         h = _cluster.connect_separate(host)
         h.load(path, engine_opts)
@@ -188,7 +191,9 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
                          window_mode=pcfg.get("window_mode", "reference"),
                          sigmoid_mode=pcfg.get("sigmoid_mode", "exact"),
                          max_grad=float(pcfg.get("max_grad", 0.0)),
-                         neg_sharing=pcfg.get("neg_sharing", "pair"))
+                         neg_sharing=pcfg.get("neg_sharing", "pair"),
+                         tile_centres=int(pcfg.get("tile_centres", 128)),
+                         tile_negatives=int(pcfg.get("tile_negatives", 64)))
         opts = engine_options_from_params(self)
         handle = open_handle_for_fit(cfg, vocab.counts, self.getParameterServerHost(),
                                      self.getNumParameterServers(), opts)

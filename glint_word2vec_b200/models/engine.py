@@ -109,8 +109,9 @@ class ShardEngine:
 
     @property
     def unfused(self) -> bool:
-        """True when the step runs as dotprod -> library all-reduce -> adjust (CPU, or transport nccl/gloo)."""
-        return (not self.is_cuda) or self.opts.transport in ("nccl", "gloo")
+        """True when the step runs as dotprod -> library all-reduce -> adjust: on CPUs, with transport nccl/gloo,
+        and for neg_sharing="tile" (library GEMMs; its tcgen05 kernel is the next step, docs/round2_tile_gemm.md)."""
+        return (not self.is_cuda) or self.opts.transport in ("nccl", "gloo") or self.cfg.neg_sharing == "tile"
 
     @property
     def vocab_size(self) -> int:
@@ -236,6 +237,8 @@ class ShardEngine:
         # every rank enumerates the same pairs, so an empty batch is empty everywhere
         if ci.shape[0] == 0:
             return stats
+        if cfg.neg_sharing == "tile":
+            return self._minibatch_tile(tokens, pos0, iteration, alpha, ci, cj, stats)
         pos = np.uint64(pos0) + ci.astype(np.uint64)
         neg = sgns.draw_negatives(cfg, self.alias, pos, slot, iteration)
         tok = tokens.astype(np.int64)
@@ -250,6 +253,48 @@ class ShardEngine:
         stats.loss = float(sgns.sgns_loss(f[:, 0], f[:, 1:], neg_mask))
         stats.max_abs_dot = float(f.abs().max())
         self.adjust(w, c, ng, gplus, gminus)
+        return stats
+
+    def _minibatch_tile(self, tokens, pos0, iteration, alpha, ci, cj, stats) -> sgns.StepStats:
+        """neg_sharing="tile" on a column shard with library GEMMs (docs/round2_tile_gemm.md): per tile
+        ``S_neg = U @ Vneg^T`` (partial over this shard's columns) -> one all-reduce of all partial dots of the
+        mini-batch -> coefficients -> ``dU = G @ Vneg``, ``dVneg = G^T @ U`` and the per-pair positive updates."""
+        cfg, dev = self.cfg, self.device
+        tok = tokens.astype(np.int64)
+        w = torch.from_numpy(tok[ci]).to(dev)
+        c = torch.from_numpy(tok[cj]).to(dev)
+        centres, m, tile = sgns.tile_terms(cfg, ci)
+        tiles, first = np.unique(tile, return_index=True)
+        bounds = np.append(first, len(centres))                        # active centres of tile k: [bounds[k], bounds[k+1])
+        tneg = sgns.tile_negatives(cfg, self.alias, pos0, tiles, iteration)
+        wa = torch.from_numpy(tok[centres]).to(dev)
+        u, vc, ua = self.syn0[w], self.syn1[c], self.syn0[wa]
+        nn = cfg.tile_negatives
+        part = torch.empty(ci.shape[0] + len(centres) * nn, dtype=torch.float32, device=dev)
+        part[:ci.shape[0]] = (u * vc).sum(-1)
+        fneg = part[ci.shape[0]:].view(len(centres), nn)
+        negs = [torch.from_numpy(tneg[k].astype(np.int64)).to(dev) for k in range(len(tiles))]
+        for k in range(len(tiles)):                                    # GEMM 1 per tile
+            a, b = int(bounds[k]), int(bounds[k + 1])
+            fneg[a:b] = ua[a:b] @ self.syn1[negs[k]].t()
+        full = self.comm.all_reduce_sum(part)                          # the Glint client-side aggregation
+        fplus, fminus = full[:ci.shape[0]], full[ci.shape[0]:].view(len(centres), nn)
+        wgt = torch.from_numpy(m.astype(np.float64) * cfg.negatives / nn).to(torch.float32).to(dev)
+        gplus = sgns.sigmoid_coeff(fplus, 1.0, alpha, cfg.sigmoid_mode, cfg.max_grad)
+        gminus = sgns.sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * wgt[:, None]
+        stats.loss = float(sgns.sgns_loss(fplus, fminus, wgt[:, None].expand_as(fminus)))
+        stats.max_abs_dot = float(full.abs().max())
+        du_neg = torch.empty_like(ua)
+        for k in range(len(tiles)):                                    # GEMMs 2 and 3 per tile, pre-update rows
+            a, b = int(bounds[k]), int(bounds[k + 1])
+            vn = self.syn1[negs[k]]
+            du_neg[a:b] = gminus[a:b] @ vn
+            negs[k] = (negs[k], gminus[a:b].t() @ ua[a:b])
+        self.syn1.index_add_(0, c, gplus[:, None] * u)
+        for idx, dvn in negs:
+            self.syn1.index_add_(0, idx, dvn)
+        self.syn0.index_add_(0, w, gplus[:, None] * vc)
+        self.syn0.index_add_(0, wa, du_neg)
         return stats
 
     # -------------------------------------------------------------- inference

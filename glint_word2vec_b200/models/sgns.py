@@ -42,11 +42,19 @@ class SGNSConfig:
     # "pair": n private negatives per (centre, context) pair - the reference's behaviour (one seed per request,
     # MLLIB:420-421).  "centre": the n negatives are drawn once per centre and shared by all of its pairs
     # (pWord2Vec-style sharing): same expected gradient, the negative rows of a centre stay hot in L2.
+    # "tile": ``tile_negatives`` negatives are drawn once per tile of ``tile_centres`` consecutive centres and
+    # shared by all of them; the negative term of centre i is weighted m_i * n / tile_negatives (m_i = number of
+    # its contexts) so that every pair still sees n negatives in expectation.  This turns the step into GEMMs
+    # (docs/round2_tile_gemm.md); implemented by the oracle and the un-fused library path, not yet by a kernel.
     neg_sharing: str = "pair"
+    tile_centres: int = 128
+    tile_negatives: int = 64
 
     def __post_init__(self):
-        if self.neg_sharing not in ("pair", "centre"):
+        if self.neg_sharing not in ("pair", "centre", "tile"):
             raise ValueError(f"unknown neg_sharing {self.neg_sharing!r}")
+        if self.tile_centres < 1 or self.tile_negatives < 1:
+            raise ValueError("tile_centres and tile_negatives must be positive")
         if self.window_mode not in ("reference", "word2vec_c"):
             raise ValueError(f"unknown window_mode {self.window_mode!r}")
         if self.sigmoid_mode not in ("exact", "table"):
@@ -131,6 +139,29 @@ def draw_negatives(cfg: SGNSConfig, alias: AliasTable, pos: np.ndarray, slot: np
     return out
 
 
+def tile_negatives(cfg: SGNSConfig, alias: AliasTable, pos0: int, tile_ids: np.ndarray,
+                   iteration: int) -> np.ndarray:
+    """[len(tile_ids), tile_negatives] shared negatives of the given tiles of a step (neg_sharing="tile").
+    Tile j covers centres [j*T, (j+1)*T) of the step; its draws are keyed by the stream position of its first
+    centre, so every shard regenerates them without traffic."""
+    nn = cfg.tile_negatives
+    pos = np.uint64(pos0) + tile_ids.astype(np.uint64) * np.uint64(cfg.tile_centres)
+    out = np.empty((len(tile_ids), nn), dtype=np.int32)
+    for c in range((nn + 1) // 2):
+        r0, r1, r2, r3 = philox.rand4(cfg.seed, philox.STREAM_NEG, pos, np.full(len(pos), c, dtype=np.uint64),
+                                      iteration)
+        out[:, 2 * c] = alias.sample(r0, r1)
+        if 2 * c + 1 < nn:
+            out[:, 2 * c + 1] = alias.sample(r2, r3)
+    return out
+
+
+def tile_terms(cfg: SGNSConfig, ci: np.ndarray):
+    """Active centres of a pair list: (step index of each active centre, its pair count m_i, its tile id)."""
+    centres, m = np.unique(ci, return_counts=True)
+    return centres, m, centres // cfg.tile_centres
+
+
 # ----------------------------------------------------------------------------
 # coefficient (sigmoid + learning rate)   -- component C3 / K3
 # ----------------------------------------------------------------------------
@@ -201,6 +232,8 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
     stats = StepStats(pairs=int(ci.shape[0]))
     if ci.shape[0] == 0:
         return stats                      # zero-pair batches are a clean no-op (Q4)
+    if cfg.neg_sharing == "tile":
+        return _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats)
     pos = np.uint64(pos0) + ci.astype(np.uint64)
     neg = draw_negatives(cfg, alias, pos, slot, iteration)
     tok = tokens.astype(np.int64)
@@ -221,6 +254,39 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
     dvc = gplus[:, None] * u
     dvn = gminus[:, :, None] * u[:, None, :]
     syn0.index_add_(0, w, du)
+    syn1.index_add_(0, c, dvc)
+    syn1.index_add_(0, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]))
+    return stats
+
+
+def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats) -> StepStats:
+    """neg_sharing="tile": positives per pair, negatives per (active centre, shared negative of its tile) with
+    weight m_i * n / N; every dot from pre-update rows, all updates summed."""
+    tok = tokens.astype(np.int64)
+    w = torch.from_numpy(tok[ci])
+    c = torch.from_numpy(tok[cj])
+    u = syn0[w]
+    vc = syn1[c]
+    fplus = (u * vc).sum(-1)
+    gplus = sigmoid_coeff(fplus, 1.0, alpha, cfg.sigmoid_mode, cfg.max_grad)
+    centres, m, tile = tile_terms(cfg, ci)
+    tiles, inv = np.unique(tile, return_inverse=True)
+    tneg = tile_negatives(cfg, alias, pos0, tiles, iteration)
+    ng = torch.from_numpy(tneg[inv].astype(np.int64))                       # [A, N]
+    wgt = torch.from_numpy(m.astype(np.float64) * cfg.negatives / cfg.tile_negatives).to(syn0.dtype)
+    wa = torch.from_numpy(tok[centres])
+    ua = syn0[wa]                                                           # [A, d]
+    vn = syn1[ng]                                                           # [A, N, d]
+    fminus = torch.einsum("ad,and->an", ua, vn)
+    gminus = sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * wgt[:, None]
+    stats.loss = float(sgns_loss(fplus, fminus, wgt[:, None].expand_as(fminus)))
+    stats.max_abs_dot = float(max(fplus.abs().max(), fminus.abs().max()))
+    du_pos = gplus[:, None] * vc
+    dvc = gplus[:, None] * u
+    du_neg = torch.einsum("an,and->ad", gminus, vn)
+    dvn = gminus[:, :, None] * ua[:, None, :]
+    syn0.index_add_(0, w, du_pos)
+    syn0.index_add_(0, wa, du_neg)
     syn1.index_add_(0, c, dvc)
     syn1.index_add_(0, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]))
     return stats

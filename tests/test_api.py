@@ -279,6 +279,23 @@ def test_fit_text_file_equals_fit_on_sentences(tmp_path):
         m2.stop()
 
 
+def test_tile_shared_negatives_keeps_the_quality_gates():
+    """neg_sharing="tile" (library-GEMM path) learns the planted structure like the default mode."""
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    m = ServerSideGlintWord2Vec(inputCol="s", outputCol="v", vectorSize=100, stepSize=0.025, seed=1, minCount=5,
+                                numParameterServers=1,
+                                parameterServerConfig={"device": "cpu", "neg_sharing": "tile", "tile_centres": 64,
+                                                       "tile_negatives": 32}).fit(synthetic_capitals_corpus())
+    try:
+        a, b = np.asarray(m.transformWord("österreich")), np.asarray(m.transformWord("wien"))
+        assert float(a @ b / np.linalg.norm(a) / np.linalg.norm(b)) > 0.9
+        q = np.asarray(m.transformWord("wien")) - a + np.asarray(m.transformWord("deutschland"))
+        assert "berlin" in [w for w, _ in m.findSynonymsArray(q, 10)]
+        assert m.getParameterServerConfig()["neg_sharing"] == "tile"
+    finally:
+        m.stop()
+
+
 def test_every_module_compiles():
     """GPU-only modules are never imported by the CPU tier; a syntax error there must still fail here."""
     import glob

@@ -274,3 +274,72 @@ def test_killed_shard_aborts_cleanly_and_training_resumes(tmp_path):
         assert np.isfinite(vecs).all()
     finally:
         h2.terminate()
+
+
+def test_tile_shared_negatives_engine_equals_oracle_and_shards_agree():
+    """neg_sharing="tile" (docs/round2_tile_gemm.md): the un-fused GEMM path of the engine == the dense oracle,
+    for one shard and for two column shards (partials summed), and the negative weights keep n negatives per
+    pair in expectation."""
+    v, d = 800, 48
+    cfg = SGNSConfig(v, d, 5, 5, seed=5, neg_sharing="tile", tile_centres=32, tile_negatives=16)
+    counts = zipf_counts(v, 10 ** 5)
+    rng = np.random.default_rng(0)
+    tokens = rng.integers(0, v, 300).astype(np.int32)
+    sid = (np.arange(300) // 25).astype(np.int32)
+
+    def make(world, rank):
+        e = ShardEngine(cfg, comm=FakeComm(rank, world), device=torch.device("cpu"),
+                        options=EngineOptions(batch_size=300))
+        e.init_weights()
+        e.set_noise(counts)
+        g = torch.Generator().manual_seed(1)
+        full1 = torch.randn(v, e.shard.padded_vector_size, generator=g) * 0.1
+        full1[:, d:] = 0
+        e.syn1 = full1[:, rank * e.shard.cols:(rank + 1) * e.shard.cols].contiguous()
+        e.syn0 = e.syn0 * 30
+        return e
+    one = make(1, 0)
+    ref0, ref1 = one.syn0[:, :d].clone(), one.syn1[:, :d].clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, one.alias, tokens, sid, 77, 0, 0.05)
+    got = one.train_step(tokens, sid, 77, 0, 0.05)
+    assert int(got[0]) == st.pairs > 0
+    assert abs(float(got[1]) - st.loss) / st.loss < 1e-5
+    assert torch.allclose(one.syn0[:, :d], ref0, atol=1e-5) and torch.allclose(one.syn1[:, :d], ref1, atol=1e-5)
+    # weights: sum over a centre's shared negatives = m_i * n
+    ci, _, _ = sgns.enumerate_pairs(cfg, tokens, sid, 77, 0)
+    centres, m, tile = sgns.tile_terms(cfg, ci)
+    assert (tile == centres // 32).all() and m.sum() == len(ci)
+    assert np.allclose(m * cfg.negatives / cfg.tile_negatives * cfg.tile_negatives, m * cfg.negatives)
+    # every shard regenerates the same shared negatives (pure function of the stream position)
+    tn = sgns.tile_negatives(cfg, one.alias, 77, np.unique(tile), 0)
+    assert tn.shape == (len(np.unique(tile)), 16)
+    assert np.array_equal(tn, sgns.tile_negatives(cfg, one.alias, 77, np.unique(tile), 0))
+
+    # two column shards through a shared in-memory all-reduce
+    class PairComm(FakeComm):
+        box = {}
+
+        def all_reduce_sum(self, t):
+            PairComm.box.setdefault("parts", []).append(t.clone())
+            return t
+    shards = [make(2, r) for r in range(2)]
+    # pass 1 records each shard's partial dots, pass 2 replays the step with their sum as the all-reduce result
+    for e in shards:
+        e.comm = PairComm(e.comm.rank, 2)
+    snap = [(e.syn0.clone(), e.syn1.clone()) for e in shards]
+    PairComm.box.clear()
+    for e in shards:
+        e.train_step(tokens, sid, 77, 0, 0.05)                     # each returns its own partial as "reduced"
+    partials = PairComm.box["parts"]
+    total = partials[0] + partials[1]
+
+    class SumComm(FakeComm):
+        def all_reduce_sum(self, t):
+            return total.clone()
+    for e, (s0, s1) in zip(shards, snap):
+        e.syn0, e.syn1 = s0, s1
+        e.comm = SumComm(e.comm.rank, 2)
+        e.train_step(tokens, sid, 77, 0, 0.05)
+    cat0 = torch.cat([e.syn0 for e in shards], 1)[:, :d]
+    cat1 = torch.cat([e.syn1 for e in shards], 1)[:, :d]
+    assert torch.allclose(cat0, ref0, atol=1e-5) and torch.allclose(cat1, ref1, atol=1e-5)
