@@ -70,9 +70,10 @@ def encode_corpus(sentences: Iterable[Sequence[str]], vocab: Vocabulary,
 
 
 def chunk_encoded(tokens: np.ndarray, offsets: np.ndarray, max_sentence_length: int) -> EncodedCorpus:
-    """Re-chunk an already encoded corpus so that no sentence exceeds the limit."""
+    """Re-chunk an already encoded corpus so that no sentence exceeds the limit; empty sentences are dropped
+    (like ``encode_corpus`` drops sentences without in-vocabulary words)."""
     lens = np.diff(offsets)
-    if lens.size == 0 or lens.max() <= max_sentence_length:
+    if lens.size == 0 or (lens.min() > 0 and lens.max() <= max_sentence_length):
         return EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64))
     new_offs = [0]
     for a, b in zip(offsets[:-1], offsets[1:]):

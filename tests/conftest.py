@@ -28,3 +28,12 @@ def corpus_sentences():
 
 
 from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus  # noqa: E402,F401
+
+
+# property tests must not be flaky in CI: derandomised example generation, no deadline, no on-disk database
+try:
+    from hypothesis import settings as _hyp_settings
+    _hyp_settings.register_profile("ci", derandomize=True, deadline=None, database=None)
+    _hyp_settings.load_profile("ci")
+except ImportError:                                   # hypothesis is optional
+    pass
