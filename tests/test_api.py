@@ -307,3 +307,24 @@ def test_every_module_compiles():
     assert len(files) > 20
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_command_line_train_query_export(tmp_path, capsys):
+    """python -m glint_word2vec_b200 train / synonyms / export."""
+    import json as _json
+    from glint_word2vec_b200.cli import main
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(s) for s in synthetic_capitals_corpus(n_sent=2500)), encoding="utf-8")
+    out = str(tmp_path / "model")
+    assert main(["train", str(corpus), "--out", out, "--vector-size", "32", "--step-size", "0.025", "--seed", "3",
+                 "--config", "device=cpu", "--config", "subsample_mode=reference"]) == 0
+    info = _json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert info["vector_size"] == 32 and info["words"] > 20 and os.path.isdir(os.path.join(out, "matrix"))
+    assert main(["synonyms", out, "wien", "no-such-word", "--num", "3", "--config", "device=cpu"]) == 0
+    lines = [_json.loads(l) for l in capsys.readouterr().out.strip().splitlines()]
+    assert lines[0]["word"] == "wien" and len(lines[0]["synonyms"]) == 3
+    assert lines[1] == {"word": "no-such-word", "error": "not in vocabulary"}
+    local = str(tmp_path / "local")
+    assert main(["export", out, local, "--config", "device=cpu"]) == 0
+    assert os.path.isdir(os.path.join(local, "data"))
