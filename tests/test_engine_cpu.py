@@ -343,3 +343,24 @@ def test_tile_shared_negatives_engine_equals_oracle_and_shards_agree():
     cat0 = torch.cat([e.syn0 for e in shards], 1)[:, :d]
     cat1 = torch.cat([e.syn1 for e in shards], 1)[:, :d]
     assert torch.allclose(cat0, ref0, atol=1e-5) and torch.allclose(cat1, ref1, atol=1e-5)
+
+
+def test_server_errors_are_reported_and_the_group_survives():
+    """A failing request (unknown op, unknown matrix, bad arguments) comes back as ServerError with the remote
+    traceback; the shard-server group keeps serving (the reference's futures time out or are swallowed, Q4)."""
+    from glint_word2vec_b200.parallel import cluster
+    h = cluster.spawn_integrated(2, "cpu", {"batch_size": 50})
+    try:
+        with pytest.raises(cluster.ServerError, match="unknown op"):
+            h._call("no_such_op")
+        with pytest.raises(cluster.ServerError):
+            h._call("pull", "no-such-matrix", np.arange(3))
+        v, d = 200, 16
+        h.create(SGNSConfig(v, d, seed=1), {"batch_size": 50}, zipf_counts(v, 10 ** 4))
+        with pytest.raises(cluster.ServerError):
+            h.pull(np.array([v + 5]))                                # row out of range
+        vec = h.pull(np.array([0, 1]))                               # still alive on both shards
+        assert vec.shape == (2, d) and np.isfinite(vec).all()
+        assert h._call("info")["world"] == 2
+    finally:
+        h.terminate()
