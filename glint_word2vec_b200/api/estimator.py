@@ -180,6 +180,9 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
         string pipeline is pointless."""
         self._validate_for_fit()
         vocab = vocab_from_counts(counts, words)
+        tokens = np.asarray(tokens)
+        if tokens.size and (int(tokens.min()) < 0 or int(tokens.max()) >= vocab.size):
+            raise ValueError(f"token ids must lie in [0, {vocab.size})")     # the kernels do not bounds-check
         corpus = chunk_encoded(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64),
                                self.getMaxSentenceLength())
         return self._fit_encoded(vocab, corpus)

@@ -298,9 +298,16 @@ class ShardEngine:
         return stats
 
     # -------------------------------------------------------------- inference
+    def _check_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """Row indices are validated on the host: the device kernels do not bounds-check (a bad index on a GPU
+        is an illegal address that kills the context, on the CPU an IndexError)."""
+        if rows.numel() and (int(rows.min()) < 0 or int(rows.max()) >= self.cfg.vocab_size):
+            raise IndexError(f"row index out of range [0, {self.cfg.vocab_size})")
+        return rows
+
     def pull(self, rows) -> torch.Tensor:
         """Full [R, d] input vectors for ``rows`` (collective)."""
-        rows = torch.as_tensor(rows, dtype=torch.int64)
+        rows = self._check_rows(torch.as_tensor(rows, dtype=torch.int64))
         if self.is_cuda and self._cuda.serve_fused:
             # the column all-gather happens inside the gather kernel (peer stores over NVLink)
             return self._cuda.serve().pull(self._cuda._rows_dev(rows))[:, :self.cfg.vector_size]
@@ -313,8 +320,11 @@ class ShardEngine:
 
     def pull_average(self, rows_flat, offsets) -> torch.Tensor:
         """Per-sentence mean of input vectors (empty sentence -> zeros), [S, d]."""
-        rows_flat = torch.as_tensor(rows_flat, dtype=torch.int64)
+        rows_flat = self._check_rows(torch.as_tensor(rows_flat, dtype=torch.int64))
         offsets = torch.as_tensor(offsets, dtype=torch.int64)
+        if offsets.numel() < 1 or int(offsets[0]) != 0 or int(offsets[-1]) != rows_flat.numel() \
+                or bool((offsets[1:] < offsets[:-1]).any()):
+            raise ValueError("offsets must be non-decreasing, start at 0 and end at len(rows_flat)")
         ns = offsets.shape[0] - 1
         if self.is_cuda and self._cuda.serve_fused:
             full = self._cuda.serve().pull_average(self._cuda._rows_dev(rows_flat), self._cuda._rows_dev(offsets))

@@ -364,3 +364,21 @@ def test_server_errors_are_reported_and_the_group_survives():
         assert h._call("info")["world"] == 2
     finally:
         h.terminate()
+
+
+def test_index_validation_on_the_host():
+    """Bad row / token indices are rejected before they can reach a kernel (which does not bounds-check)."""
+    v, d = 100, 8
+    e = ShardEngine(SGNSConfig(v, d, seed=1), device=torch.device("cpu"))
+    e.init_weights()
+    with pytest.raises(IndexError):
+        e.pull(torch.tensor([0, v]))
+    with pytest.raises(IndexError):
+        e.pull_average(torch.tensor([-1]), torch.tensor([0, 1]))
+    with pytest.raises(ValueError):
+        e.pull_average(torch.tensor([1, 2]), torch.tensor([0, 3]))
+    from glint_word2vec_b200 import ServerSideGlintWord2Vec
+    est = ServerSideGlintWord2Vec(inputCol="s", outputCol="v", vectorSize=8, numParameterServers=1,
+                                  parameterServerConfig={"device": "cpu"})
+    with pytest.raises(ValueError):
+        est.fitEncoded(np.array([0, 1, 7], dtype=np.int32), np.array([0, 3]), np.array([5, 4, 3]))
