@@ -385,6 +385,9 @@ class ShardEngine:
         Returns (indices [Q, k], similarities [Q, k]) on the CPU.
         """
         q = torch.as_tensor(queries, dtype=torch.float32).reshape(-1, self.cfg.vector_size)
+        if q.shape[0] == 0:                                   # no queries: nothing to launch (and no collective)
+            kk = min(k, self.cfg.vocab_size)
+            return torch.empty(0, kk, dtype=torch.int64), torch.empty(0, kk, dtype=torch.float32)
         qn = q.norm(dim=1, keepdim=True)
         q = torch.where(qn > 0, q / qn.clamp(min=1e-30), q)       # snrm2 / sscal (MLLIB:593-595)
         k = min(k, self.cfg.vocab_size)
