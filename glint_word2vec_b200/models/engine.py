@@ -402,12 +402,12 @@ class ShardEngine:
         return idx, sim
 
     # ------------------------------------------------------------ persistence
-    def shard_arrays(self) -> Dict[str, np.ndarray]:
-        """This rank's real (un-padded) column slices as numpy arrays."""
+    def shard_tensors(self) -> Dict[str, torch.Tensor]:
+        """This rank's real (un-padded) column slices as tensor views on the engine's device (no copy)."""
         sh = self.shard
-        out = {"syn0": self.syn0[:, :sh.real_cols].detach().cpu().numpy()}
+        out = {"syn0": self.syn0[:, :sh.real_cols].detach()}
         if self.syn1 is not None and self.opts.store_syn1:
-            out["syn1"] = self.syn1[:, :sh.real_cols].detach().cpu().numpy()
+            out["syn1"] = self.syn1[:, :sh.real_cols].detach()
         return out
 
     def load_columns(self, name: str, col_start: int, block: np.ndarray):
@@ -423,6 +423,10 @@ class ShardEngine:
         lo = max(col_start, sh.col_start)
         hi = min(col_start + block.shape[1], sh.col_start + sh.real_cols)
         if hi > lo:
-            src = torch.from_numpy(np.array(block[:, lo - col_start:hi - col_start], dtype=np.float32, order="C"))
-            target[:, lo - sh.col_start:hi - sh.col_start] = src.to(self.device)
+            # row chunks: the (usually memory-mapped) file never has to fit in host memory at once
+            step = max(1, (256 << 20) // ((hi - lo) * 4))
+            for r0 in range(0, v, step):
+                r1 = min(v, r0 + step)
+                src = torch.from_numpy(np.array(block[r0:r1, lo - col_start:hi - col_start], dtype=np.float32, order="C"))
+                target[r0:r1, lo - sh.col_start:hi - sh.col_start] = src.to(self.device)
         self._norms = None

@@ -34,6 +34,42 @@ def _matrix_dir(path: str) -> str:
     return os.path.join(path, "matrix")
 
 
+CHUNK_BYTES = 256 << 20          # rows move between device and file in pieces of this size
+
+
+def _save_npy_streamed(t, filename: str):
+    """Write a 2-D float32 tensor (any device, possibly a column slice) as a standard ``.npy`` file without ever
+    holding more than two chunks on the host: device -> pinned staging buffer -> file, the copy of chunk i+1
+    overlapping the write of chunk i."""
+    import torch
+    from numpy.lib import format as npformat
+    rows, cols = int(t.shape[0]), int(t.shape[1])
+    with open(filename, "wb") as f:
+        npformat.write_array_header_1_0(f, {"descr": "<f4", "fortran_order": False, "shape": (rows, cols)})
+        if rows == 0 or cols == 0:
+            return
+        step = max(1, CHUNK_BYTES // (cols * 4))
+        cuda = t.is_cuda
+        bufs = [torch.empty(min(step, rows), cols, dtype=torch.float32, pin_memory=cuda) for _ in range(2)]
+        evs = [torch.cuda.Event() if cuda else None for _ in range(2)]
+
+        def fetch(i, lo):
+            n = min(step, rows - lo)
+            bufs[i][:n].copy_(t[lo:lo + n], non_blocking=cuda)
+            if cuda:
+                evs[i].record()
+            return n
+        lo, i = 0, 0
+        n = fetch(i, lo)
+        while lo < rows:
+            nxt = lo + n
+            n_next = fetch(1 - i, nxt) if nxt < rows else 0
+            if cuda:
+                evs[i].synchronize()
+            f.write(memoryview(bufs[i][:n].numpy()))          # contiguous row block of the staging buffer
+            lo, n, i = nxt, n_next, 1 - i
+
+
 def save_matrix(engine: ShardEngine, path: str, extra: Optional[dict] = None):
     """Collective: every rank writes its slices, rank 0 writes the metadata."""
     mdir = _matrix_dir(path)
@@ -42,11 +78,10 @@ def save_matrix(engine: ShardEngine, path: str, extra: Optional[dict] = None):
         os.makedirs(mdir, exist_ok=True)
     comm.barrier()
     sh = engine.shard
-    arrays = engine.shard_arrays()
     entry = {"rank": sh.rank, "col_start": sh.col_start, "cols": sh.real_cols}
-    for name, arr in arrays.items():
+    for name, t in engine.shard_tensors().items():
         fn = f"{name}.{sh.rank:02d}of{sh.world:02d}.npy"
-        np.save(os.path.join(mdir, fn), np.ascontiguousarray(arr, dtype=np.float32))
+        _save_npy_streamed(t, os.path.join(mdir, fn))
         entry[name] = fn
     entries = comm.gather_objects(entry, dst=0)
     if comm.rank == 0:

@@ -382,3 +382,18 @@ def test_index_validation_on_the_host():
                                   parameterServerConfig={"device": "cpu"})
     with pytest.raises(ValueError):
         est.fitEncoded(np.array([0, 1, 7], dtype=np.int32), np.array([0, 3]), np.array([5, 4, 3]))
+
+
+def test_streamed_matrix_io_round_trip_in_small_chunks(tmp_path, monkeypatch):
+    """Shards are written and read in row chunks (never a full host copy); tiny chunk size forces the loop."""
+    monkeypatch.setattr(matrix_io, "CHUNK_BYTES", 4096)
+    v, d = 777, 20
+    e = ShardEngine(SGNSConfig(v, d, seed=2), device=torch.device("cpu"))
+    e.init_weights()
+    e.syn1 = torch.randn(v, e.shard.cols)
+    e.syn1[:, d:] = 0
+    matrix_io.save_matrix(e, str(tmp_path / "m"))
+    raw = np.load(str(tmp_path / "m" / "matrix" / "syn0.00of01.npy"))
+    assert raw.shape == (v, d) and np.array_equal(raw, e.syn0[:, :d].numpy())
+    back = matrix_io.load_matrix(str(tmp_path / "m"), Comm(), torch.device("cpu"))
+    assert torch.equal(back.syn0, e.syn0) and torch.equal(back.syn1, e.syn1)
