@@ -342,6 +342,22 @@ def test_topk_threshold_filter_is_exact(monkeypatch):
     assert ir[0].tolist() == list(range(v - 1, v - 1 - k, -1))
 
 
+def test_matrix_io_streams_from_and_to_the_device(tmp_path, monkeypatch):
+    """save_matrix / load_matrix move the shard through a pinned double buffer in row chunks."""
+    dev = _dev()
+    from glint_word2vec_b200.models import matrix_io
+    from glint_word2vec_b200.parallel.comm import Comm
+    monkeypatch.setattr(matrix_io, "CHUNK_BYTES", 64 << 10)          # many chunks
+    v, d = 5003, 100
+    eng, _ = _make_engine(dev, v, d)
+    eng.syn1 = (torch.randn(v, eng.shard.cols) * (torch.arange(eng.shard.cols) < d)).to(dev)
+    matrix_io.save_matrix(eng, str(tmp_path / "m"))
+    raw = np.load(str(tmp_path / "m" / "matrix" / "syn1.00of01.npy"))
+    assert raw.shape == (v, d) and np.array_equal(raw, eng.syn1[:, :d].cpu().numpy())
+    back = matrix_io.load_matrix(str(tmp_path / "m"), Comm(), dev)
+    assert back.syn0.is_cuda and torch.equal(back.syn0, eng.syn0) and torch.equal(back.syn1, eng.syn1)
+
+
 def test_fit_on_gpu_golden(corpus_sentences):
     """Scenario 1/10/12 of the reference spec on the device path (SPEC:83-106,290-352)."""
     _dev()
