@@ -20,7 +20,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 
-CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "sgns_kernels.cu", "sgns_pipe.cu", "sgns_group.cu", "sgns_group_multi.cu", "sgns_pipe_multi.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu", "serve_fused.cu"]
+CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "sgns_kernels.cu", "sgns_pipe.cu", "sgns_group.cu", "sgns_group_multi.cu", "sgns_pipe_multi.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu", "serve_fused.cu", "umma_probe.cu", "sgns_tile.cu"]
+CPP_SOURCES = ["bindings.cpp", "bindings_tile.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 
@@ -65,13 +66,14 @@ def build_cuda(force=False, verbose=False) -> str:
         inc += ["-isystem", p]
     inc += ["-isystem", sysconfig.get_paths()["include"]]
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
-    bsrc = os.path.join(CSRC, "bindings.cpp")
-    bobj = os.path.join(BUILD, "bindings.o")
-    objs.append(bobj)
-    if force or _newer([bsrc] + headers, bobj):
-        jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
-                     "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H", "-I", CSRC] + inc +
-                    ["-c", bsrc, "-o", bobj])
+    for cpp in CPP_SOURCES:
+        bsrc = os.path.join(CSRC, cpp)
+        bobj = os.path.join(BUILD, cpp.replace(".cpp", ".o"))
+        objs.append(bobj)
+        if force or _newer([bsrc] + headers, bobj):
+            jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
+                         "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H", "-I", CSRC] + inc +
+                        ["-c", bsrc, "-o", bobj])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(lambda c: _run(c, verbose), jobs))

@@ -499,7 +499,10 @@ void serve_push_block(ServeCtx& c, Tensor src, std::vector<int64_t> dst_ptrs) {
 
 }  // namespace
 
+void register_tile_bindings(py::module& m);      // bindings_tile.cpp
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    register_tile_bindings(m);
     py::class_<ServeCtx>(m, "ServeCtx")
         .def(py::init<int64_t, int64_t, std::vector<int64_t>, Tensor, Tensor>())
         .def("barrier", &ServeCtx::barrier)

@@ -38,4 +38,10 @@ void launch_scores_rows(const float* syn0, long long V, int K, const float* qs, 
 void launch_topk_merge(float* cand_v, const long long* cand_i, int ncand, int Q, int k, float* out_v,
                        long long* out_i, cudaStream_t s);
 
+// umma_probe.cu: descriptor probes (tests only)
+int launch_umma_probe(const uint8_t* image, int image_bytes, const unsigned long long* ops, int n_ops, float* out,
+                      int ncols, cudaStream_t stream);
+int launch_gather4_probe(const float* table, long long rows, int cols, const int* row_idx, int n4, int col, int box_cols,
+                         int bytes_per_op, int swizzle32, uint8_t* out, cudaStream_t stream);
+
 }  // namespace gw2v

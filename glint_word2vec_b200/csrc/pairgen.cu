@@ -16,6 +16,7 @@
 // All decisions are bit-identical to models/sgns.py (enumerate_pairs / draw_negatives).
 #include "common.cuh"
 #include "launchers.h"
+#include "sgns_tile.h"
 
 namespace gw2v {
 
@@ -188,6 +189,21 @@ void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, 
                                                                          alias, vocab, seed_lo, seed_hi, iteration,
                                                                          pos0, window, negatives, slots,
                                                                          pairgen_desc_ints(negatives), share_centre, desc);
+}
+
+// window masks + total pair count only: what the tensor-core tile kernel needs (it derives the pairs from the masks)
+void launch_paircount(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, uint32_t seed_lo,
+                      uint32_t seed_hi, uint32_t iteration, unsigned long long pos0, int window, int window_mode,
+                      uint32_t* cinfo, int* pair_off, int* n_pairs, int* tile_ws, float* stats, cudaStream_t stream) {
+    if (max_tokens <= 0) {
+        cudaMemsetAsync(n_pairs, 0, sizeof(int), stream);
+        if (stats) cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream);
+        return;
+    }
+    const int grid = (max_tokens + PC_TILE - 1) / PC_TILE;
+    pair_count_kernel<<<grid, PC_THREADS, 0, stream>>>(tokens, sent_id, n_tokens, seed_lo, seed_hi, iteration, pos0,
+                                                       window, window_mode, cinfo, pair_off, tile_ws);
+    pair_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_ws, grid, n_pairs, stats);
 }
 
 }  // namespace gw2v

@@ -1,0 +1,510 @@
+// sgns_tile: the SGNS training step on the 5th-generation tensor cores (neg_sharing = "tile").
+//
+// Reference hot path: dotprod -> (sum of the partial dots over the column shards) -> sigmoid / learning rate ->
+// adjust (MLLIB:417-429 + the Glint server ops [G]).  With the reference's per-pair private negatives every dot is
+// a distinct row pair and there is no GEMM; with the negatives shared by a TILE of T = 128 consecutive centres
+// (models/sgns.py, neg_sharing="tile": NN negatives per tile, negative term of centre i weighted m_i * n / NN) the
+// step of a tile is GEMM-shaped over gathered rows:
+//
+//     U = syn0[centres]              [128 x K]      (K = this shard's columns)
+//     V = syn1[contexts ; negatives] [R   x K]      R = 160 context rows (128 + 2 x 16 halo) + NN
+//     S     = U . V^T                [128 x R]      pass A  (tcgen05, tf32, accumulated in TMEM over K chunks)
+//     G     = mask * (label - sigmoid(S)) * alpha * weight     epilogue 1: band of the context block + NN block
+//     dUneg = Gneg . Vneg [128 x K], dVneg = Gneg^T . U [NN x K]   pass B (tcgen05)
+//     dUpos, dVctx : the <= 2(window-1) positive terms per centre  pass B (CUDA cores, rows read from the same
+//                                                                  shared-memory stage) -> red.global.add.v4.f32
+//
+// Data path per CTA (persistent, one CTA per SM, warp specialised):
+//   warp 5      producer   per 32-column chunk: (128 + R) / 4 x cp.async.bulk.tensor ... tile::gather4 (TMA) pull the
+//                          U and V rows by vocabulary index into a ring stage.  Pass A uses SWIZZLE_128B tensor maps
+//                          (K-major tf32 operands); pass B re-gathers the chunk (L2 hits) through
+//                          SWIZZLE_128B_ATOM_32B maps because MN-major tf32 operands exist only in that layout
+//                          (benchmarks/probe_umma*.py pins every descriptor used here against numpy on the GPU)
+//   warp 4      MMA        one elected lane issues tcgen05.mma kind::tf32; tcgen05.commit releases stages /
+//                          publishes accumulators through mbarriers
+//   warps 0-3   epilogue   tcgen05.ld S -> coefficients -> Gneg (both layouts) + band coefficients in shared memory;
+//                          tcgen05.ld dUneg / dVneg chunks + positive terms -> 16-byte RED into syn0 / syn1
+// Duplicate words inside a tile are separate rows whose updates are summed from PRE-update values: exactly the
+// reference's mini-batch semantics with batchSize = 128 (MLLIB:417-425).  Across tiles the updates are asynchronous
+// (Hogwild), as between the reference's partitions (MLLIB:392).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "sgns_params.h"
+#include "sgns_tile.h"
+
+namespace gw2v {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TL_T = 128;                  // centres per tile (UMMA M)
+constexpr int TL_HALO = 16;                // context halo rows on each side of the tile
+constexpr int TL_CTX = TL_T + 2 * TL_HALO; // 160 context rows
+constexpr int TL_BK = 32;                  // floats per K chunk: one 128-byte swizzle row
+constexpr int TL_EPI_THREADS = 128;
+constexpr int TL_MMA_WARP = 4;
+constexpr int TL_PROD_WARP = 5;
+constexpr int TL_THREADS = 192;
+constexpr int TL_BLOCK_BYTES = TL_T * 128;   // one [128 x 32 floats] swizzled block: 16 KB
+constexpr int TL_ACC_COL0 = 256;           // TMEM: S in columns [0, R), pass-B accumulators from column 256
+constexpr int TL_ACC_STRIDE = 64;          // dUneg 32 | dVneg 32
+constexpr int TL_GB_STRIDE = 25;           // floats per centre in the band-coefficient array (24 slots + pad)
+constexpr int TL_GBAND_BYTES = 13 * 1024;  // 128 * 25 * 4 = 12800, padded to keep the stages 1024-byte aligned
+constexpr int TL_MAXSTAGE = 4;
+
+template <int R> struct TileCfg {
+    static constexpr int NN = R - TL_CTX;                      // shared negatives per tile
+    static constexpr int NB = NN / 32;                         // 32-column blocks of Gneg
+    static constexpr int GK_BYTES = NB * TL_BLOCK_BYTES;       // Gneg, K-major SWIZZLE_128B        (A of dUneg)
+    static constexpr int G32_BYTES = NB * TL_BLOCK_BYTES;      // Gneg, SWIZZLE_128B_BASE32B        (A^T of dVneg)
+    static constexpr int V_STAGE_BYTES = R * 128;
+    static constexpr int STAGE_BYTES = TL_BLOCK_BYTES + V_STAGE_BYTES;
+    static constexpr int NSTAGE = (NN <= 32) ? 4 : 3;
+    static constexpr int META_INTS = TL_T + R + TL_T;          // utok | vtok | cinfo
+    static constexpr int SMEM_BYTES = 1024 + GK_BYTES + G32_BYTES + TL_GBAND_BYTES + NSTAGE * STAGE_BYTES +
+                                      2 * META_INTS * 4 + 512;
+};
+
+struct TileArgs {
+    SgnsParams p;
+    const uint32_t* cinfo;        // [T] window masks from pair_count_kernel
+    const int* tile_negs;         // [ntiles_max, NN]
+    const int* n_pairs;           // device scalar (pair_tile_scan_kernel)
+    const float* row_scale0;      // optional per-row update scale of syn0 / syn1 (hot-row damping), or null
+    const float* row_scale1;
+    float* dbg;                   // optional debug dump of tile 0: S [128 x R] (band window + negatives)
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+}  // namespace
+
+template <int R>
+__global__ void __launch_bounds__(TL_THREADS, 1)
+sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                 const __grid_constant__ CUtensorMap tm0s, const __grid_constant__ CUtensorMap tm1s, const TileArgs a) {
+    using C = TileCfg<R>;
+    constexpr int NN = C::NN;
+    const SgnsParams& p = a.p;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smGK = base;                                         // NB blocks [128 centres x 32 negs], SWIZZLE_128B
+    uint8_t* smG32 = smGK + C::GK_BYTES;                          // the same values, SWIZZLE_128B_BASE32B
+    float* smBand = reinterpret_cast<float*>(smG32 + C::G32_BYTES);   // [128][25] coefficients of the positive pairs
+    uint8_t* smStage = reinterpret_cast<uint8_t*>(smBand) + TL_GBAND_BYTES;   // NSTAGE x { U 16 KB | V R x 128 B }
+    int* smMeta = reinterpret_cast<int*>(smStage + C::NSTAGE * C::STAGE_BYTES);     // 2 x META_INTS
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smMeta + 2 * C::META_INTS);
+    uint64_t* full = bars;            // [4] TMA bytes landed
+    uint64_t* empty = bars + 4;       // [4] MMAs reading the stage retired
+    uint64_t* epi_done = bars + 8;    // [4] epilogue finished reading the stage (pass B uses only)
+    uint64_t* s_full = bars + 12;     // S accumulator complete
+    uint64_t* g_ready = bars + 13;    // coefficients written to shared memory (128 epilogue threads)
+    uint64_t* acc_full = bars + 14;   // [2] pass-B accumulators of a chunk complete
+    uint64_t* acc_empty = bars + 16;  // [2] ... drained by the epilogue (128)
+    uint64_t* meta_full = bars + 18;  // [2] tile meta loaded
+    uint64_t* tile_done = bars + 20;  // [2] epilogue finished the tile (128): meta buffer reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int K = p.K;
+    const int NC = (K + TL_BK - 1) / TL_BK;
+    const int T = *p.n_tokens;
+    const int ntiles = (T + TL_T - 1) / TL_T;
+
+    // ---------------------------------------------------------------- one-time setup
+    if (warp == TL_PROD_WARP && elect_one()) {
+        tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); tma_prefetch_desc(&tm0s); tma_prefetch_desc(&tm1s);
+    }
+    if (warp == TL_MMA_WARP) {
+        if (elect_one()) {
+            for (int s = 0; s < TL_MAXSTAGE; ++s) {
+                mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(epi_done + s, TL_EPI_THREADS);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(g_ready, TL_EPI_THREADS);
+            for (int x = 0; x < 2; ++x) {
+                mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_EPI_THREADS);
+                mbar_init(meta_full + x, 1); mbar_init(tile_done + x, TL_EPI_THREADS);
+            }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == TL_PROD_WARP) {
+        // =========================================================== producer: tile meta + TMA row gathers
+        int stage = 0; uint32_t phase = 0;
+        uint32_t b_uses[TL_MAXSTAGE] = {0, 0, 0, 0};                 // pass-B uses of each stage so far
+        uint32_t last_b = 0;                                         // bit s: the current occupant of stage s is a pass-B chunk
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int mb = it & 1;
+            int* meta = smMeta + mb * C::META_INTS;
+            if (it >= 2) mbar_wait(tile_done + mb, ((it >> 1) - 1) & 1, 10);
+            const int t0 = tile * TL_T;
+            for (int r = lane; r < TL_T; r += 32) {
+                const int pos = t0 + r;
+                meta[r] = pos < T ? __ldg(p.tokens + pos) : 0;
+                meta[TL_T + R + r] = pos < T ? (int)__ldg(a.cinfo + pos) : 0;
+            }
+            for (int r = lane; r < TL_CTX; r += 32) {
+                const int pos = t0 - TL_HALO + r;
+                meta[TL_T + r] = (pos >= 0 && pos < T) ? __ldg(p.tokens + pos) : 0;
+            }
+            for (int r = lane; r < NN; r += 32) meta[TL_T + TL_CTX + r] = __ldg(a.tile_negs + (size_t)tile * NN + r);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(meta_full + mb);
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait(empty + stage, phase ^ 1, 11);
+                    if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, (b_uses[stage] - 1) & 1, 12);
+                    uint8_t* st = smStage + (size_t)stage * C::STAGE_BYTES;
+                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)C::STAGE_BYTES);
+                    __syncwarp();
+                    for (int g = lane; g < (TL_T + R) / 4; g += 32) {
+                        const int* ids = meta + 4 * g;              // utok (32 groups), ctx (40 groups), negatives
+                        const CUtensorMap* tm;
+                        if (g < TL_T / 4) tm = pass == 0 ? &tm0 : &tm0s;                         // U: pass B MN-major
+                        else if (g < (TL_T + TL_CTX) / 4) tm = &tm1;                             // contexts: SW128 both passes
+                        else tm = pass == 0 ? &tm1 : &tm1s;                                      // negatives: pass B MN-major
+                        tma_gather4(st + g * 512, tm, c * TL_BK, ids[0], ids[1], ids[2], ids[3], full + stage);
+                    }
+                    __syncwarp();
+                    if (pass == 1) { last_b |= 1u << stage; b_uses[stage]++; } else { last_b &= ~(1u << stage); }
+                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == TL_MMA_WARP) {
+        // =========================================================== MMA issuer
+        const uint32_t idescS = make_idesc_tf32(TL_T, R, 0, 0);          // S     = U . V^T       (K-major, K-major)
+        const uint32_t idescU = make_idesc_tf32(TL_T, TL_BK, 0, 1);      // dUneg = Gneg . Vneg   (K-major, MN-major)
+        const uint32_t idescV = make_idesc_tf32(TL_T, TL_BK, 1, 1);      // dVneg = Gneg^T . U    (MN-major, MN-major)
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        uint32_t gc = 0;                                                 // running pass-B chunk counter
+        const uint32_t gk_addr = smem_u32(smGK), g32_addr = smem_u32(smG32);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            // ---- pass A
+            for (int c = 0; c < NC; ++c) {
+                mbar_wait(full + stage, phase, 20);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
+                    const uint64_t ad = make_sw128_desc(st, 16, 1024);
+                    const uint64_t bd = make_sw128_desc(st + TL_BLOCK_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < TL_BK / 8; ++k)
+                        umma_tf32(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idescS, (c > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty + stage);
+                    if (c == NC - 1) umma_commit(s_full);
+                }
+                __syncwarp();
+                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            // ---- coefficients of this tile are in shared memory
+            mbar_wait(g_ready, it & 1, 21);
+            tc_fence_after();
+            // ---- pass B
+            for (int c = 0; c < NC; ++c, ++gc) {
+                const int acc = gc & 1;
+                mbar_wait(full + stage, phase, 22);
+                mbar_wait(acc_empty + acc, ((gc >> 1) & 1) ^ 1, 23);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t vneg = st + TL_BLOCK_BYTES + TL_CTX * 128;
+                    const uint32_t d0 = tmem + TL_ACC_COL0 + acc * TL_ACC_STRIDE;
+                    // dUneg chunk [128 x 32] = Gneg [128 x NN] . Vneg chunk [NN x 32]
+#pragma unroll
+                    for (int kk = 0; kk < NN / 8; ++kk) {
+                        const uint64_t ad = make_sw128_desc(gk_addr + (kk >> 2) * TL_BLOCK_BYTES + (kk & 3) * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc(vneg + kk * 1024, 1024, 512, 1);
+                        umma_tf32(d0, ad, bd, idescU, kk > 0 ? 1u : 0u);
+                    }
+                    // dVneg chunk [NN (of M = 128) x 32] = Gneg^T . U chunk; rows >= NN read past Gneg and are ignored
+#pragma unroll 4
+                    for (int kk = 0; kk < TL_T / 8; ++kk) {
+                        const uint64_t ad = make_smem_desc(g32_addr + kk * 1024, TL_BLOCK_BYTES, 512, 1);
+                        const uint64_t bd = make_smem_desc(st + kk * 1024, 1024, 512, 1);
+                        umma_tf32(d0 + 32, ad, bd, idescV, kk > 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty + stage);
+                    umma_commit(acc_full + acc);
+                }
+                __syncwarp();
+                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // =========================================================== epilogue warps 0..3 (TMEM lane quadrant = warp)
+        const int q = warp;
+        const int row = q * 32 + lane;                                   // centre index in the tile / TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t gk_addr = smem_u32(smGK), g32_addr = smem_u32(smG32);
+        const float nratio = (float)p.negatives / (float)NN;
+        const int win = (p.window_mode == 0) ? p.window - 1 : p.window;  // farthest context offset
+        float loss = 0.f, maxdot = 0.f;
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        uint32_t gc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int mb = it & 1;
+            const int* meta = smMeta + mb * C::META_INTS;
+            const int* cinf = meta + TL_T + R;
+            mbar_wait(meta_full + mb, (it >> 1) & 1, 30);
+            const uint32_t info = (uint32_t)cinf[row];
+            const uint32_t mask = info & 0xFFFFFFu;
+            const int lo = -(int)(info >> 24);
+            const int m = __popc(mask);
+            const float wneg = (float)m * nratio;
+            for (int c = 0; c < NC; ++c)                                 // pass-A chunks go by without the epilogue
+                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+            // every epilogue thread is done with the previous tile's band coefficients before they are overwritten
+            asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory");
+            mbar_wait(s_full, it & 1, 31);
+            tc_fence_after();
+            // ---- band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {
+                uint32_t x[16];
+                tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int off = 16 * h + j - TL_HALO - lane;         // context offset of this column for this centre
+                    const int bit = off - lo;
+                    const bool on = bit >= 0 && bit < 24 && ((mask >> bit) & 1u);
+                    const float f = __uint_as_float(x[j]);
+                    if (on) {
+                        smBand[row * TL_GB_STRIDE + bit] = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
+                        if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                    }
+                    if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = f;
+                }
+            }
+            // ---- shared negatives: columns [160, 160 + NN) -> Gneg in both operand layouts
+#pragma unroll 1
+            for (int h = 0; h < NN / 16; ++h) {
+                uint32_t x[16];
+                tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
+                tmem_ld_wait();
+                float g[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float f = __uint_as_float(x[j]);
+                    g[j] = m > 0 ? wneg * sgns_coeff(f, 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
+                    if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                    if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + TL_CTX + 16 * h + j] = f;
+                }
+                const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int c16 = (h & 1) * 4 + cq;                    // 16-byte chunk of the 32-float block row
+                    st_shared_v4(gk_addr + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4),
+                                 g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                    const int c32 = (c16 >> 1) ^ (row & 3);              // 32-byte chunk, 4-row period
+                    st_shared_v4(g32_addr + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16),
+                                 g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                }
+            }
+            fence_proxy_async_smem();          // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
+            tc_fence_before();
+            mbar_arrive(g_ready);
+            // epilogue threads read each other's band coefficients below
+            asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory");
+
+            // ---- rows this thread updates
+            const int utok = meta[row];
+            const bool u_on = m > 0;
+            const float su = (a.row_scale0 != nullptr && u_on) ? __ldg(a.row_scale0 + utok) : 1.f;
+            float* urow = p.syn0 + (size_t)utok * K;
+            const int ntok = row < NN ? meta[TL_T + TL_CTX + row] : 0;
+            const float sn = (a.row_scale1 != nullptr && row < NN) ? __ldg(a.row_scale1 + ntok) : 1.f;
+            float* nrow = p.syn1 + (size_t)ntok * K;
+            // ---- pass B: accumulators + positive terms -> 16-byte atomics
+            for (int c = 0; c < NC; ++c, ++gc) {
+                const int acc = gc & 1;
+                const int col0 = c * TL_BK;
+                const uint32_t stU = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
+                const uint32_t stV = stU + TL_BLOCK_BYTES;
+                mbar_wait(full + stage, phase, 32);
+                // (1) context rows r = row and row + 128 (< 160): dV_r = sum over the centres that have r as a context
+#pragma unroll 1
+                for (int rr = row; rr < TL_CTX; rr += TL_T) {
+                    const int pos = tile * TL_T - TL_HALO + rr;
+                    if (pos < 0 || pos >= T) continue;
+                    const int ci0 = max(0, rr - TL_HALO - win), ci1 = min(TL_T - 1, rr - TL_HALO + win);
+                    float av[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) av[e] = 0.f;
+                    bool any = false;
+                    for (int ci = ci0; ci <= ci1; ++ci) {
+                        const uint32_t inf = (uint32_t)cinf[ci];
+                        const int bit = (rr - TL_HALO - ci) + (int)(inf >> 24);      // offset - lo
+                        if (bit < 0 || bit >= 24 || !((inf >> bit) & 1u)) continue;
+                        any = true;
+                        const float g = smBand[ci * TL_GB_STRIDE + bit];
+                        const uint32_t ur = stU + (uint32_t)ci * 128;                // U row ci, SWIZZLE_128B_ATOM_32B
+#pragma unroll
+                        for (int c32 = 0; c32 < 4; ++c32) {
+                            const uint32_t ph = ur + (uint32_t)((c32 ^ (ci & 3)) * 32);
+                            const float4 x0 = ld_shared_v4(ph), x1 = ld_shared_v4(ph + 16);
+                            av[8 * c32 + 0] = fmaf(g, x0.x, av[8 * c32 + 0]); av[8 * c32 + 1] = fmaf(g, x0.y, av[8 * c32 + 1]);
+                            av[8 * c32 + 2] = fmaf(g, x0.z, av[8 * c32 + 2]); av[8 * c32 + 3] = fmaf(g, x0.w, av[8 * c32 + 3]);
+                            av[8 * c32 + 4] = fmaf(g, x1.x, av[8 * c32 + 4]); av[8 * c32 + 5] = fmaf(g, x1.y, av[8 * c32 + 5]);
+                            av[8 * c32 + 6] = fmaf(g, x1.z, av[8 * c32 + 6]); av[8 * c32 + 7] = fmaf(g, x1.w, av[8 * c32 + 7]);
+                        }
+                    }
+                    if (any && !(p.debug & 1)) {
+                        const int vtok = meta[TL_T + rr];
+                        const float sv = a.row_scale1 != nullptr ? __ldg(a.row_scale1 + vtok) : 1.f;
+                        float* vrow = p.syn1 + (size_t)vtok * K + col0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col0 + 4 * j < K)
+                                red_add_v4(vrow + 4 * j, sv * av[4 * j], sv * av[4 * j + 1], sv * av[4 * j + 2], sv * av[4 * j + 3]);
+                    }
+                }
+                // (2) centre row: dU = dUneg (tensor cores) + sum over its contexts g * v
+                mbar_wait(acc_full + acc, (gc >> 1) & 1, 33);
+                tc_fence_after();
+                const uint32_t d0 = lane_addr + TL_ACC_COL0 + acc * TL_ACC_STRIDE;
+                {
+                    uint32_t x[32];
+                    tmem_ld32(d0, x);                                    // warp-collective: never predicated
+                    tmem_ld_wait();
+                    float au[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) au[e] = __uint_as_float(x[e]);
+                    uint32_t mm = mask;
+                    while (mm) {
+                        const int bit = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int j = row + TL_HALO + lo + bit;          // context row of this pair
+                        const float g = smBand[row * TL_GB_STRIDE + bit];
+                        const uint32_t vr = stV + (uint32_t)j * 128;     // V row j, SWIZZLE_128B
+#pragma unroll
+                        for (int cq = 0; cq < 8; ++cq) {
+                            const float4 v = ld_shared_v4(vr + (uint32_t)((cq ^ (j & 7)) << 4));
+                            au[4 * cq + 0] = fmaf(g, v.x, au[4 * cq + 0]); au[4 * cq + 1] = fmaf(g, v.y, au[4 * cq + 1]);
+                            au[4 * cq + 2] = fmaf(g, v.z, au[4 * cq + 2]); au[4 * cq + 3] = fmaf(g, v.w, au[4 * cq + 3]);
+                        }
+                    }
+                    if (u_on && !(p.debug & 1)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col0 + 4 * j < K)
+                                red_add_v4(urow + col0 + 4 * j, su * au[4 * j], su * au[4 * j + 1], su * au[4 * j + 2], su * au[4 * j + 3]);
+                    }
+                }
+                // (3) shared negatives: lanes [0, NN) of the dVneg accumulator (warp-uniform condition)
+                if (q < NN / 32) {
+                    uint32_t x[32];
+                    tmem_ld32(d0 + 32, x);
+                    tmem_ld_wait();
+                    if (!(p.debug & 1)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col0 + 4 * j < K)
+                                red_add_v4(nrow + col0 + 4 * j, sn * __uint_as_float(x[4 * j]), sn * __uint_as_float(x[4 * j + 1]),
+                                           sn * __uint_as_float(x[4 * j + 2]), sn * __uint_as_float(x[4 * j + 3]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty + acc);
+                mbar_arrive(epi_done + stage);
+                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            mbar_arrive(tile_done + mb);
+        }
+        if (p.compute_loss) {
+            loss = warp_sum(loss);
+            maxdot = warp_max(maxdot);
+            if (lane == 0) {
+                if (loss != 0.f) atomicAdd(p.stats + 1, loss);
+                atomicMax(reinterpret_cast<int*>(p.stats + 2), __float_as_int(maxdot));
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)T; p.stats[0] = (float)(*a.n_pairs); }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TL_MMA_WARP) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------ shared negatives of the tiles
+// negs[tile, 2c], negs[tile, 2c+1] = alias samples of philox(seed, NEG | iteration, pos0 + tile * 128, c): bit-identical
+// to models/sgns.py::tile_negatives, identical on every shard (no index ever crosses NVLink)
+__global__ void tile_negs_kernel(const int* __restrict__ n_tokens, const int2* __restrict__ alias, int vocab,
+                                 uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0, int nn,
+                                 int* __restrict__ out) {
+    const int T = *n_tokens;
+    const int ntiles = (T + TL_T - 1) / TL_T;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = nn / 2;
+    const int tile = gid / half, c = gid - tile * half;
+    if (tile >= ntiles) return;
+    const uint4 r = rand4(seed_lo, seed_hi, stream_word(STREAM_NEG, iteration), pos0 + (unsigned long long)tile * TL_T, (uint32_t)c);
+    out[(size_t)tile * nn + 2 * c] = alias_sample(alias, (uint32_t)vocab, r.x, r.y);
+    out[(size_t)tile * nn + 2 * c + 1] = alias_sample(alias, (uint32_t)vocab, r.z, r.w);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+bool sgns_tile_supported(int K, int window, int negatives, int tile_centres, int tile_negatives) {
+    return K % 4 == 0 && K >= 4 && K <= 4096 && window >= 1 && window <= 11 && negatives >= 1 && tile_centres == TL_T &&
+           (tile_negatives == 32 || tile_negatives == 64);
+}
+
+int sgns_tile_max_tiles(int max_tokens) { return (max_tokens + TL_T - 1) / TL_T; }
+
+template <int R>
+static int launch_tile_r(const SgnsParams& p, const TileLaunch& l, cudaStream_t stream) {
+    using C = TileCfg<R>;
+    CUtensorMap tm0, tm1, tm0s, tm1s;
+    const uint64_t V = (uint64_t)p.vocab, K = (uint64_t)p.K;
+    if (!make_tensormap_f32(&tm0, p.syn0, V, K, K, TL_BK, 1, false)) return 2;
+    if (!make_tensormap_f32(&tm1, p.syn1, V, K, K, TL_BK, 1, false)) return 2;
+    if (!make_tensormap_f32(&tm0s, p.syn0, V, K, K, TL_BK, 1, true)) return 2;
+    if (!make_tensormap_f32(&tm1s, p.syn1, V, K, K, TL_BK, 1, true)) return 2;
+    TileArgs a{};
+    a.p = p;
+    a.cinfo = l.cinfo; a.tile_negs = l.tile_negs; a.n_pairs = l.n_pairs;
+    a.row_scale0 = l.row_scale0; a.row_scale1 = l.row_scale1; a.dbg = l.dbg;
+    auto kern = sgns_tile_kernel<R>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    kern<<<l.grid, TL_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tm0s, tm1s, a);
+    return 0;
+}
+
+int launch_sgns_tile(const SgnsParams& p, const TileLaunch& l, cudaStream_t stream) {
+    if (l.max_tokens <= 0) return 0;
+    const int nn = l.tile_negatives;
+    const int max_tiles = sgns_tile_max_tiles(l.max_tokens);
+    const int total = max_tiles * (nn / 2);
+    tile_negs_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p.n_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi, p.iteration,
+                                                              p.pos0, nn, l.tile_negs);
+    if (nn == 32) return launch_tile_r<192>(p, l, stream);
+    if (nn == 64) return launch_tile_r<224>(p, l, stream);
+    return 1;
+}
+
+}  // namespace gw2v

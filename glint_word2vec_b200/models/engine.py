@@ -109,9 +109,9 @@ class ShardEngine:
 
     @property
     def unfused(self) -> bool:
-        """True when the step runs as dotprod -> library all-reduce -> adjust: on CPUs, with transport nccl/gloo,
-        and for neg_sharing="tile" (library GEMMs; its tcgen05 kernel is the next step, docs/round2_tile_gemm.md)."""
-        return (not self.is_cuda) or self.opts.transport in ("nccl", "gloo") or self.cfg.neg_sharing == "tile"
+        """True when the step runs as dotprod -> library all-reduce -> adjust: on CPUs and with transport nccl/gloo
+        (neg_sharing="tile" then uses library GEMMs; on GPUs it is the tcgen05 kernel csrc/sgns_tile.cu)."""
+        return (not self.is_cuda) or self.opts.transport in ("nccl", "gloo")
 
     @property
     def vocab_size(self) -> int:

@@ -89,6 +89,15 @@ class CudaShardOps:
         if self._loopback > 1:
             self.debug |= 8
         self._share_centre = 1 if engine.cfg.neg_sharing == "centre" else 0
+        # neg_sharing="tile": the tcgen05 kernel (csrc/sgns_tile.cu); there is no other device implementation of it
+        self._tile_mode = engine.cfg.neg_sharing == "tile"
+        if self._tile_mode and not _C.sgns_tile_supported(self.K, engine.cfg.window, engine.cfg.negatives,
+                                                          engine.cfg.tile_centres, engine.cfg.tile_negatives):
+            raise ValueError('neg_sharing="tile" on a GPU needs tile_centres=128, tile_negatives in {32, 64}, '
+                             "window <= 11 and a multiple of 4 columns per shard")
+        self.row_scale0: Optional[torch.Tensor] = None     # optional per-row update scales (hot-row damping)
+        self.row_scale1: Optional[torch.Tensor] = None
+        self.tile_dbg: Optional[torch.Tensor] = None       # tests: dot products of tile 0
         # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self.exp_table = None
         if engine.cfg.sigmoid_mode == "table":
@@ -155,8 +164,13 @@ class CudaShardOps:
         self.pg_cinfo = torch.empty(cap, dtype=torch.int32, device=d)
         self.pg_off = torch.empty(cap, dtype=torch.int32, device=d)
         self.pg_npairs = torch.zeros(1, dtype=torch.int32, device=d)
-        self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd, dtype=torch.int32, device=d)
         self.pg_tiles = torch.zeros(int(_C.pairgen_max_blocks(cap)) + 1, dtype=torch.int32, device=d)
+        if self._tile_mode:
+            # tensor-core tile kernel: no pair descriptors, only the shared negatives of every tile
+            self.pg_desc = None
+            self.tile_negs = torch.zeros(int(_C.sgns_tile_max_tiles(cap)) * cfg.tile_negatives, dtype=torch.int32, device=d)
+        else:
+            self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd, dtype=torch.int32, device=d)
         self._cap = cap
 
     # ------------------------------------------------------------------ cross-shard exchange
@@ -304,7 +318,7 @@ class CudaShardOps:
         cfg = self.cfg
         e = self.e
         self._ensure_capacity(t)
-        if self.world > 1 and self._xchg is None:
+        if self.world > 1 and self._xchg is None and not self._tile_mode:
             self._setup_exchange()
         if self.subsample_active:
             _C.subsample_compact(tok_dev, sid_dev, t, self.keep_dev, int(cfg.seed), int(iteration),
@@ -321,9 +335,21 @@ class CudaShardOps:
         stats = self._stats_ring[self._stats_i]
         pairs_path = (self.world > 1 and self._xchg["variant"] == 3) or \
             (self.world == 1 and getattr(self, "_variant", None) == 3)
-        if not pairs_path:
+        if not pairs_path and not self._tile_mode:
             stats.zero_()                 # the pairs path zeroes them inside pair_tile_scan_kernel (one launch less)
         wm = WINDOW_MODES[cfg.window_mode]
+        if self._tile_mode:
+            if self.world > 1:
+                raise NotImplementedError('neg_sharing="tile" over column shards')
+            if not hasattr(self, "_tile_grid"):
+                self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
+            _C.sgns_step_tile(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                              int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                              float(cfg.max_grad), self.compute_loss, self._tile_grid, self.debug, self.pg_cinfo,
+                              self.pg_off, self.pg_npairs, self.pg_tiles, self.tile_negs, cfg.tile_negatives,
+                              self.exp_table, self.row_scale0, self.row_scale1, self.tile_dbg)
+            self.launches += 4            # pair_count, pair_tile_scan, tile_negs, sgns_tile
+            return stats
         if self.world > 1 and self._xchg["variant"] == 3:
             x = self._xchg
             _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
