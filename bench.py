@@ -44,7 +44,8 @@ def parse():
                     help="word2vec = the intended formula of MLLIB:375-377 at --subsample-ratio; reference = the "
                          "reference's effective behaviour (integer-division bug: nothing is dropped)")
     ap.add_argument("--subsample-ratio", type=float, default=1e-4)
-    ap.add_argument("--neg-sharing", default="pair", choices=["pair", "centre"],
+    ap.add_argument("--tile-negatives", type=int, default=64, help="shared negatives per 128-centre tile (neg-sharing tile)")
+    ap.add_argument("--neg-sharing", default="pair", choices=["pair", "centre", "tile"],
                     help="pair = n private negatives per pair (reference semantics, the headline); centre = the n "
                          "negatives of a centre are shared by its pairs (optional mode)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -141,7 +142,8 @@ def main():
     from glint_word2vec_b200.parallel.comm import Comm, TorchDistComm
 
     comm = TorchDistComm() if world > 1 else Comm()
-    cfg = SGNSConfig(args.vocab, args.dim, args.window, args.neg, seed=1, neg_sharing=args.neg_sharing)
+    cfg = SGNSConfig(args.vocab, args.dim, args.window, args.neg, seed=1, neg_sharing=args.neg_sharing,
+                     tile_negatives=args.tile_negatives)
     opts = EngineOptions(subsample_mode=args.subsample, subsample_ratio=args.subsample_ratio)
     eng = ShardEngine(cfg, comm=comm, device=dev, options=opts)
     eng.init_weights()
@@ -257,7 +259,10 @@ def main():
         "subsample": args.subsample + (" t=%g" % args.subsample_ratio if args.subsample == "word2vec" else " (inert)"),
         "pairs_counted": "trained (centre, context) pairs after sub-sampling",
         "neg_sharing": "pair (n private negatives per (centre, context) pair)" if args.neg_sharing == "pair"
-        else "centre (the n negatives of a centre are shared by its pairs) - NOT the reference semantics",
+        else ("centre (the n negatives of a centre are shared by its pairs) - NOT the reference semantics"
+              if args.neg_sharing == "centre" else
+              "tile (%d negatives shared by each tile of 128 centres, weighted m_i*n/N; tcgen05 kernel) - NOT the "
+              "reference semantics" % args.tile_negatives),
         "l2": "inputs (2 x %.1f GB embedding shards per GPU) far larger than the 126 MB L2; no flush needed"
               % (args.vocab * eng.shard.cols * 4 / 1e9),
     }

@@ -15,15 +15,16 @@
 //                                                                  shared-memory stage) -> red.global.add.v4.f32
 //
 // Data path per CTA (persistent, one CTA per SM, warp specialised):
-//   warp 5      producer   per 32-column chunk: (128 + R) / 4 x cp.async.bulk.tensor ... tile::gather4 (TMA) pull the
-//                          U and V rows by vocabulary index into a ring stage.  Pass A uses SWIZZLE_128B tensor maps
+//   warps 9-12  producers  per 32-column chunk: (128 + R) / 4 x cp.async.bulk.tensor ... tile::gather4 (TMA) pull the
+//                          U and V rows by vocabulary index into a ring stage (one copy per lane, four warps issue).  Pass A uses SWIZZLE_128B tensor maps
 //                          (K-major tf32 operands); pass B re-gathers the chunk (L2 hits) through
 //                          SWIZZLE_128B_ATOM_32B maps because MN-major tf32 operands exist only in that layout
 //                          (benchmarks/probe_umma*.py pins every descriptor used here against numpy on the GPU)
-//   warp 4      MMA        one elected lane issues tcgen05.mma kind::tf32; tcgen05.commit releases stages /
+//   warp 8      MMA        one elected lane issues tcgen05.mma kind::tf32; tcgen05.commit releases stages /
 //                          publishes accumulators through mbarriers
-//   warps 0-3   epilogue   tcgen05.ld S -> coefficients -> Gneg (both layouts) + band coefficients in shared memory;
-//                          tcgen05.ld dUneg / dVneg chunks + positive terms -> 16-byte RED into syn0 / syn1
+//   warps 0-7   epilogue   two groups of four warps (TMEM lane quadrant = warp % 4).  tcgen05.ld S -> coefficients ->
+//                          Gneg (both layouts) + band coefficients in shared memory; the pass-B chunks alternate
+//                          between the groups: tcgen05.ld dUneg / dVneg + positive terms -> 16-byte RED into syn0 / syn1
 // Duplicate words inside a tile are separate rows whose updates are summed from PRE-update values: exactly the
 // reference's mini-batch semantics with batchSize = 128 (MLLIB:417-425).  Across tiles the updates are asynchronous
 // (Hogwild), as between the reference's partitions (MLLIB:392).
@@ -42,15 +43,17 @@ constexpr int TL_T = 128;                  // centres per tile (UMMA M)
 constexpr int TL_HALO = 16;                // context halo rows on each side of the tile
 constexpr int TL_CTX = TL_T + 2 * TL_HALO; // 160 context rows
 constexpr int TL_BK = 32;                  // floats per K chunk: one 128-byte swizzle row
-constexpr int TL_EPI_THREADS = 128;
-constexpr int TL_MMA_WARP = 4;
-constexpr int TL_PROD_WARP = 5;
-constexpr int TL_THREADS = 192;
+constexpr int TL_EPI_THREADS = 256;        // two epilogue groups of 4 warps (TMEM lane quadrant = warp % 4)
+constexpr int TL_GROUP_THREADS = 128;
+constexpr int TL_MMA_WARP = 8;
+constexpr int TL_PROD_WARP0 = 9;           // producer warps 9..12
+constexpr int TL_NPROD = 4;
+constexpr int TL_THREADS = 13 * 32;
 constexpr int TL_BLOCK_BYTES = TL_T * 128;   // one [128 x 32 floats] swizzled block: 16 KB
 constexpr int TL_ACC_COL0 = 256;           // TMEM: S in columns [0, R), pass-B accumulators from column 256
 constexpr int TL_ACC_STRIDE = 64;          // dUneg 32 | dVneg 32
-constexpr int TL_GB_STRIDE = 25;           // floats per centre in the band-coefficient array (24 slots + pad)
-constexpr int TL_GBAND_BYTES = 13 * 1024;  // 128 * 25 * 4 = 12800, padded to keep the stages 1024-byte aligned
+constexpr int TL_GB_STRIDE = 25;           // floats per row in the band-coefficient arrays (<= 24 slots + pad)
+constexpr int TL_BAND_BYTES = 17 * 1024;   // [160][25] coefficients by context row + [160] masks, padded to 1 KB
 constexpr int TL_MAXSTAGE = 4;
 
 template <int R> struct TileCfg {
@@ -61,9 +64,12 @@ template <int R> struct TileCfg {
     static constexpr int V_STAGE_BYTES = R * 128;
     static constexpr int STAGE_BYTES = TL_BLOCK_BYTES + V_STAGE_BYTES;
     static constexpr int NSTAGE = (NN <= 32) ? 4 : 3;
+    static constexpr int NGROUPS = (TL_T + R) / 4;             // gather4 copies per stage
     static constexpr int META_INTS = TL_T + R + TL_T;          // utok | vtok | cinfo
-    static constexpr int SMEM_BYTES = 1024 + GK_BYTES + G32_BYTES + TL_GBAND_BYTES + NSTAGE * STAGE_BYTES +
+    static constexpr int SMEM_BYTES = 1024 + GK_BYTES + G32_BYTES + TL_BAND_BYTES + NSTAGE * STAGE_BYTES +
                                       2 * META_INTS * 4 + 512;
+    static_assert(NGROUPS % TL_NPROD == 0, "gather groups must split evenly over the producer warps");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct TileArgs {
@@ -82,11 +88,25 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory"); }
 
 }  // namespace
 
@@ -101,20 +121,25 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smGK = base;                                         // NB blocks [128 centres x 32 negs], SWIZZLE_128B
     uint8_t* smG32 = smGK + C::GK_BYTES;                          // the same values, SWIZZLE_128B_BASE32B
-    float* smBand = reinterpret_cast<float*>(smG32 + C::G32_BYTES);   // [128][25] coefficients of the positive pairs
-    uint8_t* smStage = reinterpret_cast<uint8_t*>(smBand) + TL_GBAND_BYTES;   // NSTAGE x { U 16 KB | V R x 128 B }
+    uint8_t* smBandRaw = smG32 + C::G32_BYTES;                    // coefficients of the positive pairs:
+    //   bandT [160][25]  coefficient of the pair (centre i, context row r = i + 16 + off) at [r][win - off]
+    //   maskT [160]      which slots of a context row are live  (dV: row r sums g * u over its centres;
+    //                                                            dU: centre i walks its own window mask)
+    uint8_t* smStage = smBandRaw + TL_BAND_BYTES;                 // NSTAGE x { U 16 KB | V R x 128 B }
     int* smMeta = reinterpret_cast<int*>(smStage + C::NSTAGE * C::STAGE_BYTES);     // 2 x META_INTS
     uint64_t* bars = reinterpret_cast<uint64_t*>(smMeta + 2 * C::META_INTS);
-    uint64_t* full = bars;            // [4] TMA bytes landed
+    uint64_t* full = bars;            // [4] TMA bytes landed (one expect_tx per producer warp)
     uint64_t* empty = bars + 4;       // [4] MMAs reading the stage retired
     uint64_t* epi_done = bars + 8;    // [4] epilogue finished reading the stage (pass B uses only)
     uint64_t* s_full = bars + 12;     // S accumulator complete
-    uint64_t* g_ready = bars + 13;    // coefficients written to shared memory (128 epilogue threads)
+    uint64_t* g_ready = bars + 13;    // coefficients written to shared memory (256 epilogue threads)
     uint64_t* acc_full = bars + 14;   // [2] pass-B accumulators of a chunk complete
-    uint64_t* acc_empty = bars + 16;  // [2] ... drained by the epilogue (128)
+    uint64_t* acc_empty = bars + 16;  // [2] ... drained by the epilogue group that owns the buffer (128)
     uint64_t* meta_full = bars + 18;  // [2] tile meta loaded
-    uint64_t* tile_done = bars + 20;  // [2] epilogue finished the tile (128): meta buffer reusable
+    uint64_t* tile_done = bars + 20;  // [2] epilogue finished the tile (256): meta buffer reusable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    const uint32_t bandT = smem_u32(smBandRaw);
+    const uint32_t maskT = bandT + TL_CTX * TL_GB_STRIDE * 4;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,18 +149,18 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     const int ntiles = (T + TL_T - 1) / TL_T;
 
     // ---------------------------------------------------------------- one-time setup
-    if (warp == TL_PROD_WARP && elect_one()) {
+    if (warp == TL_PROD_WARP0 && elect_one()) {
         tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); tma_prefetch_desc(&tm0s); tma_prefetch_desc(&tm1s);
     }
     if (warp == TL_MMA_WARP) {
         if (elect_one()) {
             for (int s = 0; s < TL_MAXSTAGE; ++s) {
-                mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(epi_done + s, TL_EPI_THREADS);
+                mbar_init(full + s, TL_NPROD); mbar_init(empty + s, 1); mbar_init(epi_done + s, TL_GROUP_THREADS);
             }
             mbar_init(s_full, 1);
             mbar_init(g_ready, TL_EPI_THREADS);
             for (int x = 0; x < 2; ++x) {
-                mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_EPI_THREADS);
+                mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_GROUP_THREADS);
                 mbar_init(meta_full + x, 1); mbar_init(tile_done + x, TL_EPI_THREADS);
             }
             mbar_fence_init();
@@ -148,8 +173,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == TL_PROD_WARP) {
-        // =========================================================== producer: tile meta + TMA row gathers
+    if (warp >= TL_PROD_WARP0) {
+        // =========================================================== producers: tile meta + TMA row gathers
+        const int pw = warp - TL_PROD_WARP0;
+        constexpr int MYG = C::NGROUPS / TL_NPROD;                   // gather4 copies of this warp per stage
         int stage = 0; uint32_t phase = 0;
         uint32_t b_uses[TL_MAXSTAGE] = {0, 0, 0, 0};                 // pass-B uses of each stage so far
         uint32_t last_b = 0;                                         // bit s: the current occupant of stage s is a pass-B chunk
@@ -157,36 +184,41 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int mb = it & 1;
             int* meta = smMeta + mb * C::META_INTS;
-            if (it >= 2) mbar_wait(tile_done + mb, ((it >> 1) - 1) & 1, 10);
-            const int t0 = tile * TL_T;
-            for (int r = lane; r < TL_T; r += 32) {
-                const int pos = t0 + r;
-                meta[r] = pos < T ? __ldg(p.tokens + pos) : 0;
-                meta[TL_T + R + r] = pos < T ? (int)__ldg(a.cinfo + pos) : 0;
+            if (pw == 0) {
+                if (it >= 2) mbar_wait(tile_done + mb, ((it >> 1) - 1) & 1, 10);
+                const int t0 = tile * TL_T;
+                for (int r = lane; r < TL_T; r += 32) {
+                    const int pos = t0 + r;
+                    meta[r] = pos < T ? __ldg(p.tokens + pos) : 0;
+                    meta[TL_T + R + r] = pos < T ? (int)__ldg(a.cinfo + pos) : 0;
+                }
+                for (int r = lane; r < TL_CTX; r += 32) {
+                    const int pos = t0 - TL_HALO + r;
+                    meta[TL_T + r] = (pos >= 0 && pos < T) ? __ldg(p.tokens + pos) : 0;
+                }
+                for (int r = lane; r < NN; r += 32) meta[TL_T + TL_CTX + r] = __ldg(a.tile_negs + (size_t)tile * NN + r);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(meta_full + mb);
             }
-            for (int r = lane; r < TL_CTX; r += 32) {
-                const int pos = t0 - TL_HALO + r;
-                meta[TL_T + r] = (pos >= 0 && pos < T) ? __ldg(p.tokens + pos) : 0;
+            mbar_wait(meta_full + mb, (it >> 1) & 1, 13);
+            // this lane's gather4 copy of every stage use of the tile: rows and tensor maps do not depend on the chunk
+            const int g = pw + TL_NPROD * lane;                      // lanes [0, MYG) are active
+            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            if (lane < MYG) {
+                const int4 ids = *reinterpret_cast<const int4*>(meta + 4 * g);       // utok (32), contexts (40), negatives
+                i0 = ids.x; i1 = ids.y; i2 = ids.z; i3 = ids.w;
             }
-            for (int r = lane; r < NN; r += 32) meta[TL_T + TL_CTX + r] = __ldg(a.tile_negs + (size_t)tile * NN + r);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(meta_full + mb);
+            const bool is_u = g < TL_T / 4, is_ctx = !is_u && g < (TL_T + TL_CTX) / 4;
             for (int pass = 0; pass < 2; ++pass) {
+                // pass B: U and the negatives through the 32-byte-atom swizzle (MN-major operands); contexts stay SW128
+                const CUtensorMap* tm = is_u ? (pass == 0 ? &tm0 : &tm0s) : (is_ctx ? &tm1 : (pass == 0 ? &tm1 : &tm1s));
                 for (int c = 0; c < NC; ++c) {
                     mbar_wait(empty + stage, phase ^ 1, 11);
                     if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, (b_uses[stage] - 1) & 1, 12);
                     uint8_t* st = smStage + (size_t)stage * C::STAGE_BYTES;
-                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)C::STAGE_BYTES);
+                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(MYG * 512));
                     __syncwarp();
-                    for (int g = lane; g < (TL_T + R) / 4; g += 32) {
-                        const int* ids = meta + 4 * g;              // utok (32 groups), ctx (40 groups), negatives
-                        const CUtensorMap* tm;
-                        if (g < TL_T / 4) tm = pass == 0 ? &tm0 : &tm0s;                         // U: pass B MN-major
-                        else if (g < (TL_T + TL_CTX) / 4) tm = &tm1;                             // contexts: SW128 both passes
-                        else tm = pass == 0 ? &tm1 : &tm1s;                                      // negatives: pass B MN-major
-                        tma_gather4(st + g * 512, tm, c * TL_BK, ids[0], ids[1], ids[2], ids[3], full + stage);
-                    }
-                    __syncwarp();
+                    if (lane < MYG) tma_gather4(st + g * 512, tm, c * TL_BK, i0, i1, i2, i3, full + stage);
                     if (pass == 1) { last_b |= 1u << stage; b_uses[stage]++; } else { last_b &= ~(1u << stage); }
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -254,9 +286,13 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             }
         }
     } else {
-        // =========================================================== epilogue warps 0..3 (TMEM lane quadrant = warp)
-        const int q = warp;
+        // =========================================================== epilogue: group 0 = warps 0-3, group 1 = warps 4-7
+        // Epilogue 1 is split by columns (group 0: band of the context block, group 1: shared negatives); the pass-B
+        // chunks alternate between the groups with the accumulator buffer (chunk gc belongs to group gc & 1).
+        const int grp = warp >> 2;
+        const int q = warp & 3;                                          // TMEM lane quadrant
         const int row = q * 32 + lane;                                   // centre index in the tile / TMEM lane
+        const int etid = threadIdx.x;                                    // 0..255
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t gk_addr = smem_u32(smGK), g32_addr = smem_u32(smG32);
         const float nratio = (float)p.negatives / (float)NN;
@@ -267,125 +303,173 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         uint32_t gc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int mb = it & 1;
-            const int* meta = smMeta + mb * C::META_INTS;
-            const int* cinf = meta + TL_T + R;
+            const uint32_t meta = smem_u32(smMeta + mb * C::META_INTS);
             mbar_wait(meta_full + mb, (it >> 1) & 1, 30);
-            const uint32_t info = (uint32_t)cinf[row];
+            const uint32_t info = ld_shared_u32(meta + (TL_T + R + row) * 4);
             const uint32_t mask = info & 0xFFFFFFu;
             const int lo = -(int)(info >> 24);
             const int m = __popc(mask);
             const float wneg = (float)m * nratio;
             for (int c = 0; c < NC; ++c)                                 // pass-A chunks go by without the epilogue
                 if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
-            // every epilogue thread is done with the previous tile's band coefficients before they are overwritten
-            asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory");
+            // every epilogue thread is done with the previous tile's coefficients before they are overwritten
+            epi_bar();
+            if (etid < TL_CTX) asm volatile("st.shared.u32 [%0], %1;" ::"r"(maskT + etid * 4), "r"(0u) : "memory");
+            epi_bar();
             mbar_wait(s_full, it & 1, 31);
             tc_fence_after();
-            // ---- band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
+            if (grp == 0) {
+                // ---- band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
 #pragma unroll 1
-            for (int h = 0; h < 4; ++h) {
-                uint32_t x[16];
-                tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
-                tmem_ld_wait();
+                for (int h = 0; h < 4; ++h) {
+                    uint32_t x[16];
+                    tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int off = 16 * h + j - TL_HALO - lane;         // context offset of this column for this centre
-                    const int bit = off - lo;
-                    const bool on = bit >= 0 && bit < 24 && ((mask >> bit) & 1u);
-                    const float f = __uint_as_float(x[j]);
-                    if (on) {
-                        smBand[row * TL_GB_STRIDE + bit] = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
-                        if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                    for (int j = 0; j < 16; ++j) {
+                        const int off = 16 * h + j - TL_HALO - lane;     // context offset of this column for this centre
+                        const int bit = off - lo;
+                        const bool on = bit >= 0 && bit < 24 && ((mask >> bit) & 1u);
+                        const float f = __uint_as_float(x[j]);
+                        if (on) {
+                            const float g = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
+                            const int cr = row + TL_HALO + off;          // context row of the pair, slot = win - off
+                            st_shared_f32(bandT + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
+                            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(maskT + cr * 4), "r"(1u << (win - off)) : "memory");
+                            if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                        }
+                        if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = f;
                     }
-                    if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = f;
                 }
-            }
-            // ---- shared negatives: columns [160, 160 + NN) -> Gneg in both operand layouts
+            } else {
+                // ---- shared negatives: columns [160, 160 + NN) -> Gneg in both operand layouts
 #pragma unroll 1
-            for (int h = 0; h < NN / 16; ++h) {
-                uint32_t x[16];
-                tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
-                tmem_ld_wait();
-                float g[16];
+                for (int h = 0; h < NN / 16; ++h) {
+                    uint32_t x[16];
+                    tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
+                    tmem_ld_wait();
+                    float g[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float f = __uint_as_float(x[j]);
-                    g[j] = m > 0 ? wneg * sgns_coeff(f, 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
-                    if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f); maxdot = fmaxf(maxdot, fabsf(f)); }
-                    if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + TL_CTX + 16 * h + j] = f;
-                }
-                const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
+                    for (int j = 0; j < 16; ++j) {
+                        const float f = __uint_as_float(x[j]);
+                        g[j] = m > 0 ? wneg * sgns_coeff(f, 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
+                        if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                        if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + TL_CTX + 16 * h + j] = f;
+                    }
+                    const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
 #pragma unroll
-                for (int cq = 0; cq < 4; ++cq) {
-                    const int c16 = (h & 1) * 4 + cq;                    // 16-byte chunk of the 32-float block row
-                    st_shared_v4(gk_addr + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4),
-                                 g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
-                    const int c32 = (c16 >> 1) ^ (row & 3);              // 32-byte chunk, 4-row period
-                    st_shared_v4(g32_addr + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16),
-                                 g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                    for (int cq = 0; cq < 4; ++cq) {
+                        const int c16 = (h & 1) * 4 + cq;                // 16-byte chunk of the 32-float block row
+                        st_shared_v4(gk_addr + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4),
+                                     g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                        const int c32 = (c16 >> 1) ^ (row & 3);          // 32-byte chunk, 4-row period
+                        st_shared_v4(g32_addr + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16),
+                                     g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                    }
                 }
             }
             fence_proxy_async_smem();          // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
             tc_fence_before();
             mbar_arrive(g_ready);
-            // epilogue threads read each other's band coefficients below
-            asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory");
+            epi_bar();                         // both groups read each other's coefficients below
 
-            // ---- rows this thread updates
-            const int utok = meta[row];
+            // ---- rows this thread updates in the chunks of its group
+            const int utok = (int)ld_shared_u32(meta + row * 4);
             const bool u_on = m > 0;
             const float su = (a.row_scale0 != nullptr && u_on) ? __ldg(a.row_scale0 + utok) : 1.f;
-            float* urow = p.syn0 + (size_t)utok * K;
-            const int ntok = row < NN ? meta[TL_T + TL_CTX + row] : 0;
+            const int ntok = row < NN ? (int)ld_shared_u32(meta + (TL_T + TL_CTX + row) * 4) : 0;
             const float sn = (a.row_scale1 != nullptr && row < NN) ? __ldg(a.row_scale1 + ntok) : 1.f;
-            float* nrow = p.syn1 + (size_t)ntok * K;
+            // context rows owned by this thread: `row` and, in warp 3 of the group, also row 128 + lane
+            uint32_t cm[2]; int ctok[2]; float cs[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int rr = x == 0 ? row : ((q == 3) ? TL_T + lane : TL_CTX);
+                cm[x] = 0; ctok[x] = 0; cs[x] = 1.f;
+                if (rr < TL_CTX) {
+                    cm[x] = ld_shared_u32(maskT + rr * 4);
+                    ctok[x] = (int)ld_shared_u32(meta + (TL_T + rr) * 4);
+                    if (a.row_scale1 != nullptr && cm[x]) cs[x] = __ldg(a.row_scale1 + ctok[x]);
+                }
+            }
             // ---- pass B: accumulators + positive terms -> 16-byte atomics
             for (int c = 0; c < NC; ++c, ++gc) {
+                if ((int)(gc & 1) != grp) {                              // the other group's chunk
+                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 const int acc = gc & 1;
                 const int col0 = c * TL_BK;
                 const uint32_t stU = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
                 const uint32_t stV = stU + TL_BLOCK_BYTES;
                 mbar_wait(full + stage, phase, 32);
-                // (1) context rows r = row and row + 128 (< 160): dV_r = sum over the centres that have r as a context
-#pragma unroll 1
-                for (int rr = row; rr < TL_CTX; rr += TL_T) {
-                    const int pos = tile * TL_T - TL_HALO + rr;
-                    if (pos < 0 || pos >= T) continue;
-                    const int ci0 = max(0, rr - TL_HALO - win), ci1 = min(TL_T - 1, rr - TL_HALO + win);
-                    float av[32];
+                // dV of one context row: sum over the centres ci = rr - 16 - win + k that have it as a context of g * u_ci
+                auto band_dv = [&](int rr, uint32_t mm, float (&av)[32]) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) av[e] = 0.f;
-                    bool any = false;
-                    for (int ci = ci0; ci <= ci1; ++ci) {
-                        const uint32_t inf = (uint32_t)cinf[ci];
-                        const int bit = (rr - TL_HALO - ci) + (int)(inf >> 24);      // offset - lo
-                        if (bit < 0 || bit >= 24 || !((inf >> bit) & 1u)) continue;
-                        any = true;
-                        const float g = smBand[ci * TL_GB_STRIDE + bit];
+                    while (mm) {
+                        const int k = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int ci = rr - TL_HALO - win + k;
+                        const float g = ld_shared_f32(bandT + (uint32_t)(rr * TL_GB_STRIDE + k) * 4);
                         const uint32_t ur = stU + (uint32_t)ci * 128;                // U row ci, SWIZZLE_128B_ATOM_32B
+                        float4 xv[8];
 #pragma unroll
                         for (int c32 = 0; c32 < 4; ++c32) {
                             const uint32_t ph = ur + (uint32_t)((c32 ^ (ci & 3)) * 32);
-                            const float4 x0 = ld_shared_v4(ph), x1 = ld_shared_v4(ph + 16);
-                            av[8 * c32 + 0] = fmaf(g, x0.x, av[8 * c32 + 0]); av[8 * c32 + 1] = fmaf(g, x0.y, av[8 * c32 + 1]);
-                            av[8 * c32 + 2] = fmaf(g, x0.z, av[8 * c32 + 2]); av[8 * c32 + 3] = fmaf(g, x0.w, av[8 * c32 + 3]);
-                            av[8 * c32 + 4] = fmaf(g, x1.x, av[8 * c32 + 4]); av[8 * c32 + 5] = fmaf(g, x1.y, av[8 * c32 + 5]);
-                            av[8 * c32 + 6] = fmaf(g, x1.z, av[8 * c32 + 6]); av[8 * c32 + 7] = fmaf(g, x1.w, av[8 * c32 + 7]);
+                            xv[2 * c32] = ld_shared_v4(ph); xv[2 * c32 + 1] = ld_shared_v4(ph + 16);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            av[4 * e + 0] = fmaf(g, xv[e].x, av[4 * e + 0]); av[4 * e + 1] = fmaf(g, xv[e].y, av[4 * e + 1]);
+                            av[4 * e + 2] = fmaf(g, xv[e].z, av[4 * e + 2]); av[4 * e + 3] = fmaf(g, xv[e].w, av[4 * e + 3]);
                         }
                     }
-                    if (any && !(p.debug & 1)) {
-                        const int vtok = meta[TL_T + rr];
-                        const float sv = a.row_scale1 != nullptr ? __ldg(a.row_scale1 + vtok) : 1.f;
-                        float* vrow = p.syn1 + (size_t)vtok * K + col0;
+                };
+                // Row updates leave as COALESCED 16-byte atomics: the 32 rows of a warp are transposed through 4 KB of
+                // shared memory (the warp's quarter of this stage's U block, dead once its MMAs and the band reads are
+                // done) so that one RED instruction covers 4 rows x 128 contiguous bytes instead of 32 scattered
+                // 16-byte pieces -- the scattered form was measured LSU-bound (profiles/r2_tile_v2_ncu.md).
+                const uint32_t scratch = stU + (uint32_t)q * 4096;
+                auto red_rows = [&](const float (&v)[32], float* mat, int tok, bool on, float scale) {
+#pragma unroll
+                    for (int cq = 0; cq < 8; ++cq)
+                        st_shared_v4(scratch + (uint32_t)lane * 128 + (uint32_t)((cq ^ (lane & 7)) << 4), scale * v[4 * cq],
+                                     scale * v[4 * cq + 1], scale * v[4 * cq + 2], scale * v[4 * cq + 3]);
+                    __syncwarp();
+                    const int tk = on ? tok : -1;
+                    const int cq = lane & 7;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int r = ps * 4 + (lane >> 3);
+                        const int rt = __shfl_sync(0xffffffffu, tk, r);
+                        const float4 x = ld_shared_v4(scratch + (uint32_t)r * 128 + (uint32_t)((cq ^ (r & 7)) << 4));
+                        if (rt >= 0 && col0 + 4 * cq < K && !(p.debug & 1))
+                            red_add_v4(mat + (size_t)rt * K + col0 + 4 * cq, x.x, x.y, x.z, x.w);
+                    }
+                    __syncwarp();
+                };
+                // (1a) context rows 128..159 (warp 3 of the group): few rows, direct scattered atomics
+                if (q == 3 && cm[1] != 0) {
+                    float av[32];
+                    band_dv(TL_T + lane, cm[1], av);
+                    if (!(p.debug & 1)) {
+                        float* vrow = p.syn1 + (size_t)ctok[1] * K + col0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (col0 + 4 * j < K)
-                                red_add_v4(vrow + 4 * j, sv * av[4 * j], sv * av[4 * j + 1], sv * av[4 * j + 2], sv * av[4 * j + 3]);
+                                red_add_v4(vrow + 4 * j, cs[1] * av[4 * j], cs[1] * av[4 * j + 1], cs[1] * av[4 * j + 2], cs[1] * av[4 * j + 3]);
                     }
                 }
-                // (2) centre row: dU = dUneg (tensor cores) + sum over its contexts g * v
+                // (1b) context rows 0..127 into registers
+                float av0[32];
+                band_dv(row, cm[0], av0);
+                // the chunk's MMAs have retired and every thread of the group is done reading U: the U block is scratch now
                 mbar_wait(acc_full + acc, (gc >> 1) & 1, 33);
                 tc_fence_after();
+                if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(TL_GROUP_THREADS) : "memory");
+                else asm volatile("bar.sync 3, %0;" ::"n"(TL_GROUP_THREADS) : "memory");
+                red_rows(av0, p.syn1, ctok[0], cm[0] != 0, cs[0]);
+                // (2) centre row: dU = dUneg (tensor cores) + sum over its contexts g * v
                 const uint32_t d0 = lane_addr + TL_ACC_COL0 + acc * TL_ACC_STRIDE;
                 {
                     uint32_t x[32];
@@ -399,35 +483,30 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         const int bit = __ffs(mm) - 1;
                         mm &= mm - 1;
                         const int j = row + TL_HALO + lo + bit;          // context row of this pair
-                        const float g = smBand[row * TL_GB_STRIDE + bit];
+                        const float g = ld_shared_f32(bandT + (uint32_t)(j * TL_GB_STRIDE + win - lo - bit) * 4);
                         const uint32_t vr = stV + (uint32_t)j * 128;     // V row j, SWIZZLE_128B
+                        float4 xv[8];
 #pragma unroll
-                        for (int cq = 0; cq < 8; ++cq) {
-                            const float4 v = ld_shared_v4(vr + (uint32_t)((cq ^ (j & 7)) << 4));
-                            au[4 * cq + 0] = fmaf(g, v.x, au[4 * cq + 0]); au[4 * cq + 1] = fmaf(g, v.y, au[4 * cq + 1]);
-                            au[4 * cq + 2] = fmaf(g, v.z, au[4 * cq + 2]); au[4 * cq + 3] = fmaf(g, v.w, au[4 * cq + 3]);
+                        for (int cq = 0; cq < 8; ++cq) xv[cq] = ld_shared_v4(vr + (uint32_t)((cq ^ (j & 7)) << 4));
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            au[4 * e + 0] = fmaf(g, xv[e].x, au[4 * e + 0]); au[4 * e + 1] = fmaf(g, xv[e].y, au[4 * e + 1]);
+                            au[4 * e + 2] = fmaf(g, xv[e].z, au[4 * e + 2]); au[4 * e + 3] = fmaf(g, xv[e].w, au[4 * e + 3]);
                         }
                     }
-                    if (u_on && !(p.debug & 1)) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (col0 + 4 * j < K)
-                                red_add_v4(urow + col0 + 4 * j, su * au[4 * j], su * au[4 * j + 1], su * au[4 * j + 2], su * au[4 * j + 3]);
-                    }
+                    red_rows(au, p.syn0, utok, u_on, su);
                 }
                 // (3) shared negatives: lanes [0, NN) of the dVneg accumulator (warp-uniform condition)
                 if (q < NN / 32) {
                     uint32_t x[32];
                     tmem_ld32(d0 + 32, x);
                     tmem_ld_wait();
-                    if (!(p.debug & 1)) {
+                    float an[32];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (col0 + 4 * j < K)
-                                red_add_v4(nrow + col0 + 4 * j, sn * __uint_as_float(x[4 * j]), sn * __uint_as_float(x[4 * j + 1]),
-                                           sn * __uint_as_float(x[4 * j + 2]), sn * __uint_as_float(x[4 * j + 3]));
-                    }
+                    for (int e = 0; e < 32; ++e) an[e] = __uint_as_float(x[e]);
+                    red_rows(an, p.syn1, ntok, true, sn);
                 }
+                fence_proxy_async_smem();      // scratch writes (generic proxy) before the next TMA fill of this stage
                 tc_fence_before();
                 mbar_arrive(acc_empty + acc);
                 mbar_arrive(epi_done + stage);
