@@ -16,7 +16,7 @@
 //
 // Data path per CTA (persistent, one CTA per SM, warp specialised):
 //   warps 9-12  producers  per 32-column chunk: (128 + R) / 4 x cp.async.bulk.tensor ... tile::gather4 (TMA) pull the
-//                          U and V rows by vocabulary index into a ring stage (one copy per lane, four warps issue).  Pass A uses SWIZZLE_128B tensor maps
+//                          U and V rows by vocabulary index into a ring stage (one copy per lane, four warps issue); the ring interleaves pass B of tile t with pass A of tile t+1.  Pass A uses SWIZZLE_128B tensor maps
 //                          (K-major tf32 operands); pass B re-gathers the chunk (L2 hits) through
 //                          SWIZZLE_128B_ATOM_32B maps because MN-major tf32 operands exist only in that layout
 //                          (benchmarks/probe_umma*.py pins every descriptor used here against numpy on the GPU)
@@ -52,7 +52,7 @@ constexpr int TL_THREADS = 13 * 32;
 constexpr int TL_BLOCK_BYTES = TL_T * 128;   // one [128 x 32 floats] swizzled block: 16 KB
 constexpr int TL_ACC_COL0 = 256;           // TMEM: S in columns [0, R), pass-B accumulators from column 256
 constexpr int TL_ACC_STRIDE = 64;          // dUneg 32 | dVneg 32
-constexpr int TL_GB_STRIDE = 25;           // floats per row in the band-coefficient arrays (<= 24 slots + pad)
+constexpr int TL_GB_STRIDE = 25;           // floats per row in the band-coefficient array (<= 23 slots + pad)
 constexpr int TL_BAND_BYTES = 17 * 1024;   // [160][25] coefficients by context row + [160] masks, padded to 1 KB
 constexpr int TL_MAXSTAGE = 4;
 
@@ -66,8 +66,15 @@ template <int R> struct TileCfg {
     static constexpr int NSTAGE = (NN <= 32) ? 4 : 3;
     static constexpr int NGROUPS = (TL_T + R) / 4;             // gather4 copies per stage
     static constexpr int META_INTS = TL_T + R + TL_T;          // utok | vtok | cinfo
-    static constexpr int SMEM_BYTES = 1024 + GK_BYTES + G32_BYTES + TL_BAND_BYTES + NSTAGE * STAGE_BYTES +
-                                      2 * META_INTS * 4 + 512;
+    // byte offsets from the 1024-aligned base
+    static constexpr int GK_OFF = 0;
+    static constexpr int G32_OFF = GK_OFF + GK_BYTES;
+    static constexpr int BAND_OFF = G32_OFF + G32_BYTES;
+    static constexpr int MASK_OFF = BAND_OFF + TL_CTX * TL_GB_STRIDE * 4;
+    static constexpr int STAGE_OFF = BAND_OFF + TL_BAND_BYTES;
+    static constexpr int META_OFF = STAGE_OFF + NSTAGE * STAGE_BYTES;
+    static constexpr int BAR_OFF = META_OFF + 3 * META_INTS * 4;
+    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + 512;
     static_assert(NGROUPS % TL_NPROD == 0, "gather groups must split evenly over the producer warps");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -82,31 +89,21 @@ struct TileArgs {
     float* dbg;                   // optional debug dump of tile 0: S [128 x R] (band window + negatives)
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float a) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) { atomicAdd(reinterpret_cast<float4*>(p), v); }
+
+// plain C++ accesses through a pointer that is still known to be shared memory (base = smem_raw + padding), so the
+// compiler emits LDS / STS and is free to batch and hoist them
+__device__ __forceinline__ float4 lds4(const uint8_t* sm, uint32_t off) { return *reinterpret_cast<const float4*>(sm + off); }
+__device__ __forceinline__ float lds1(const uint8_t* sm, uint32_t off) { return *reinterpret_cast<const float*>(sm + off); }
+__device__ __forceinline__ uint32_t ldsu(const uint8_t* sm, uint32_t off) { return *reinterpret_cast<const uint32_t*>(sm + off); }
+__device__ __forceinline__ void sts4(uint8_t* sm, uint32_t off, float4 v) { *reinterpret_cast<float4*>(sm + off) = v; }
+__device__ __forceinline__ void sts1(uint8_t* sm, uint32_t off, float v) { *reinterpret_cast<float*>(sm + off) = v; }
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TL_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void fma4(float (&acc)[32], int e, float g, float4 x) {
+    acc[4 * e + 0] = fmaf(g, x.x, acc[4 * e + 0]); acc[4 * e + 1] = fmaf(g, x.y, acc[4 * e + 1]);
+    acc[4 * e + 2] = fmaf(g, x.z, acc[4 * e + 2]); acc[4 * e + 3] = fmaf(g, x.w, acc[4 * e + 3]);
+}
 
 }  // namespace
 
@@ -118,16 +115,14 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     constexpr int NN = C::NN;
     const SgnsParams& p = a.p;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smGK = base;                                         // NB blocks [128 centres x 32 negs], SWIZZLE_128B
-    uint8_t* smG32 = smGK + C::GK_BYTES;                          // the same values, SWIZZLE_128B_BASE32B
-    uint8_t* smBandRaw = smG32 + C::G32_BYTES;                    // coefficients of the positive pairs:
-    //   bandT [160][25]  coefficient of the pair (centre i, context row r = i + 16 + off) at [r][win - off]
-    //   maskT [160]      which slots of a context row are live  (dV: row r sums g * u over its centres;
-    //                                                            dU: centre i walks its own window mask)
-    uint8_t* smStage = smBandRaw + TL_BAND_BYTES;                 // NSTAGE x { U 16 KB | V R x 128 B }
-    int* smMeta = reinterpret_cast<int*>(smStage + C::NSTAGE * C::STAGE_BYTES);     // 2 x META_INTS
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smMeta + 2 * C::META_INTS);
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1024-aligned, still a shared pointer
+    const uint32_t sm_addr = smem_u32(sm);
+    // GK   : NB blocks [128 centres x 32 negatives], SWIZZLE_128B          G32 : the same values, SWIZZLE_128B_BASE32B
+    // BAND : bandT [160][25]: coefficient of the pair (centre i, context row r = i + 16 + off) at [r][win - off]
+    // MASK : maskT [160]: live slots of a context row   (dV: row r sums g * u over its centres; dU: centre i walks its mask)
+    // STAGE: NSTAGE x { U block 16 KB | V rows R x 128 B }                 META: 3 x { utok 128 | vtok R | cinfo 128 }
+    int* smMeta = reinterpret_cast<int*>(sm + C::META_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);
     uint64_t* full = bars;            // [4] TMA bytes landed (one expect_tx per producer warp)
     uint64_t* empty = bars + 4;       // [4] MMAs reading the stage retired
     uint64_t* epi_done = bars + 8;    // [4] epilogue finished reading the stage (pass B uses only)
@@ -135,11 +130,9 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint64_t* g_ready = bars + 13;    // coefficients written to shared memory (256 epilogue threads)
     uint64_t* acc_full = bars + 14;   // [2] pass-B accumulators of a chunk complete
     uint64_t* acc_empty = bars + 16;  // [2] ... drained by the epilogue group that owns the buffer (128)
-    uint64_t* meta_full = bars + 18;  // [2] tile meta loaded
-    uint64_t* tile_done = bars + 20;  // [2] epilogue finished the tile (256): meta buffer reusable
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-    const uint32_t bandT = smem_u32(smBandRaw);
-    const uint32_t maskT = bandT + TL_CTX * TL_GB_STRIDE * 4;
+    uint64_t* meta_full = bars + 18;  // [3] tile meta loaded (three buffers: the producers run up to two tiles ahead)
+    uint64_t* tile_done = bars + 21;  // [3] epilogue finished the tile (256): meta buffer reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -159,10 +152,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             }
             mbar_init(s_full, 1);
             mbar_init(g_ready, TL_EPI_THREADS);
-            for (int x = 0; x < 2; ++x) {
-                mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_GROUP_THREADS);
-                mbar_init(meta_full + x, 1); mbar_init(tile_done + x, TL_EPI_THREADS);
-            }
+            for (int x = 0; x < 2; ++x) { mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_GROUP_THREADS); }
+            for (int x = 0; x < 3; ++x) { mbar_init(meta_full + x, 1); mbar_init(tile_done + x, TL_EPI_THREADS); }
             mbar_fence_init();
         }
         __syncwarp();
@@ -178,14 +169,19 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         const int pw = warp - TL_PROD_WARP0;
         constexpr int MYG = C::NGROUPS / TL_NPROD;                   // gather4 copies of this warp per stage
         int stage = 0; uint32_t phase = 0;
-        uint32_t b_uses[TL_MAXSTAGE] = {0, 0, 0, 0};                 // pass-B uses of each stage so far
+        uint32_t b_uses = 0;                                         // pass-B uses of each stage so far, 8 bits per stage
         uint32_t last_b = 0;                                         // bit s: the current occupant of stage s is a pass-B chunk
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int mb = it & 1;
+        const int g = pw + TL_NPROD * lane;                          // this lane's gather4 copy; lanes [0, MYG) are active
+        const bool is_u = g < TL_T / 4, is_ctx = !is_u && g < (TL_T + TL_CTX) / 4;
+        // pass A: everything SWIZZLE_128B (K-major); pass B: U and the negatives through the 32-byte-atom swizzle
+        const CUtensorMap* tmA = is_u ? &tm0 : &tm1;
+        const CUtensorMap* tmB = is_u ? &tm0s : (is_ctx ? &tm1 : &tm1s);
+        int4 idc = make_int4(0, 0, 0, 0), idn = make_int4(0, 0, 0, 0);     // row ids of the current / next tile
+        auto load_meta = [&](int tile, int it) {                     // producer warp 0: stage the tile's indices
+            const int mb = it % 3;
             int* meta = smMeta + mb * C::META_INTS;
             if (pw == 0) {
-                if (it >= 2) mbar_wait(tile_done + mb, ((it >> 1) - 1) & 1, 10);
+                if (it >= 3) mbar_wait(tile_done + mb, ((it / 3) - 1) & 1, 10);
                 const int t0 = tile * TL_T;
                 for (int r = lane; r < TL_T; r += 32) {
                     const int pos = t0 + r;
@@ -200,29 +196,37 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(meta_full + mb);
             }
-            mbar_wait(meta_full + mb, (it >> 1) & 1, 13);
-            // this lane's gather4 copy of every stage use of the tile: rows and tensor maps do not depend on the chunk
-            const int g = pw + TL_NPROD * lane;                      // lanes [0, MYG) are active
-            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-            if (lane < MYG) {
-                const int4 ids = *reinterpret_cast<const int4*>(meta + 4 * g);       // utok (32), contexts (40), negatives
-                i0 = ids.x; i1 = ids.y; i2 = ids.z; i3 = ids.w;
+            mbar_wait(meta_full + mb, (it / 3) & 1, 13);
+            int4 ids = make_int4(0, 0, 0, 0);
+            if (lane < MYG) ids = *reinterpret_cast<const int4*>(meta + 4 * g);       // utok (32), contexts (40), negatives
+            return ids;
+        };
+        auto fill = [&](const CUtensorMap* tm, const int4& ids, int c, bool pass_b) {
+            mbar_wait(empty + stage, phase ^ 1, 11);
+            if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, ((b_uses >> (8 * stage)) - 1) & 1, 12);
+            uint8_t* st = sm + C::STAGE_OFF + stage * C::STAGE_BYTES;
+            if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(MYG * 512));
+            __syncwarp();
+            if (lane < MYG) tma_gather4(st + g * 512, tm, c * TL_BK, ids.x, ids.y, ids.z, ids.w, full + stage);
+            if (pass_b) { last_b |= 1u << stage; b_uses += 1u << (8 * stage); } else { last_b &= ~(1u << stage); }
+            if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+        };
+        // Ring order: A(first tile), then per tile t: B(t, 0), A(t+1, 0), B(t, 1), A(t+1, 1), ... -- the S GEMM of the
+        // next tile is fed while the epilogue works on this tile's updates.
+        int it = 0;
+        if ((int)blockIdx.x < ntiles) {
+            idc = load_meta(blockIdx.x, 0);
+            for (int c = 0; c < NC; ++c) fill(tmA, idc, c, false);
+        }
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int next = tile + gridDim.x;
+            const bool has_next = next < ntiles;
+            if (has_next) idn = load_meta(next, it + 1);
+            for (int c = 0; c < NC; ++c) {
+                fill(tmB, idc, c, true);
+                if (has_next) fill(tmA, idn, c, false);
             }
-            const bool is_u = g < TL_T / 4, is_ctx = !is_u && g < (TL_T + TL_CTX) / 4;
-            for (int pass = 0; pass < 2; ++pass) {
-                // pass B: U and the negatives through the 32-byte-atom swizzle (MN-major operands); contexts stay SW128
-                const CUtensorMap* tm = is_u ? (pass == 0 ? &tm0 : &tm0s) : (is_ctx ? &tm1 : (pass == 0 ? &tm1 : &tm1s));
-                for (int c = 0; c < NC; ++c) {
-                    mbar_wait(empty + stage, phase ^ 1, 11);
-                    if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, (b_uses[stage] - 1) & 1, 12);
-                    uint8_t* st = smStage + (size_t)stage * C::STAGE_BYTES;
-                    if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(MYG * 512));
-                    __syncwarp();
-                    if (lane < MYG) tma_gather4(st + g * 512, tm, c * TL_BK, i0, i1, i2, i3, full + stage);
-                    if (pass == 1) { last_b |= 1u << stage; b_uses[stage]++; } else { last_b &= ~(1u << stage); }
-                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
-                }
-            }
+            idc = idn;
         }
     } else if (warp == TL_MMA_WARP) {
         // =========================================================== MMA issuer
@@ -232,36 +236,37 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         uint32_t gc = 0;                                                 // running pass-B chunk counter
-        const uint32_t gk_addr = smem_u32(smGK), g32_addr = smem_u32(smG32);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            // ---- pass A
-            for (int c = 0; c < NC; ++c) {
-                mbar_wait(full + stage, phase, 20);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
-                    const uint64_t ad = make_sw128_desc(st, 16, 1024);
-                    const uint64_t bd = make_sw128_desc(st + TL_BLOCK_BYTES, 16, 1024);
+        const uint32_t gk_addr = sm_addr + C::GK_OFF, g32_addr = sm_addr + C::G32_OFF;
+        auto mma_a = [&](int c) {                                       // S += U chunk . V chunk^T
+            mbar_wait(full + stage, phase, 20);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t st = sm_addr + C::STAGE_OFF + stage * C::STAGE_BYTES;
+                const uint64_t ad = make_sw128_desc(st, 16, 1024);
+                const uint64_t bd = make_sw128_desc(st + TL_BLOCK_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < TL_BK / 8; ++k)
-                        umma_tf32(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idescS, (c > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(empty + stage);
-                    if (c == NC - 1) umma_commit(s_full);
-                }
-                __syncwarp();
-                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                for (int k = 0; k < TL_BK / 8; ++k)
+                    umma_tf32(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idescS, (c > 0 || k > 0) ? 1u : 0u);
+                umma_commit(empty + stage);
+                if (c == NC - 1) umma_commit(s_full);
             }
-            // ---- coefficients of this tile are in shared memory
+            __syncwarp();
+            if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+        };
+        if ((int)blockIdx.x < ntiles)
+            for (int c = 0; c < NC; ++c) mma_a(c);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const bool has_next = tile + (int)gridDim.x < ntiles;
+            // ---- coefficients of this tile are in shared memory (and S has been drained: the next tile may overwrite it)
             mbar_wait(g_ready, it & 1, 21);
             tc_fence_after();
-            // ---- pass B
             for (int c = 0; c < NC; ++c, ++gc) {
                 const int acc = gc & 1;
                 mbar_wait(full + stage, phase, 22);
                 mbar_wait(acc_empty + acc, ((gc >> 1) & 1) ^ 1, 23);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t st = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t st = sm_addr + C::STAGE_OFF + stage * C::STAGE_BYTES;
                     const uint32_t vneg = st + TL_BLOCK_BYTES + TL_CTX * 128;
                     const uint32_t d0 = tmem + TL_ACC_COL0 + acc * TL_ACC_STRIDE;
                     // dUneg chunk [128 x 32] = Gneg [128 x NN] . Vneg chunk [NN x 32]
@@ -283,6 +288,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 }
                 __syncwarp();
                 if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                if (has_next) mma_a(c);                                  // pass A of the next tile, same chunk index
             }
         }
     } else {
@@ -294,7 +300,6 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         const int row = q * 32 + lane;                                   // centre index in the tile / TMEM lane
         const int etid = threadIdx.x;                                    // 0..255
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const uint32_t gk_addr = smem_u32(smGK), g32_addr = smem_u32(smG32);
         const float nratio = (float)p.negatives / (float)NN;
         const int win = (p.window_mode == 0) ? p.window - 1 : p.window;  // farthest context offset
         float loss = 0.f, maxdot = 0.f;
@@ -302,19 +307,21 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         int it = 0;
         uint32_t gc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int mb = it & 1;
-            const uint32_t meta = smem_u32(smMeta + mb * C::META_INTS);
-            mbar_wait(meta_full + mb, (it >> 1) & 1, 30);
-            const uint32_t info = ld_shared_u32(meta + (TL_T + R + row) * 4);
+            const int mb = it % 3;
+            const uint32_t meta = C::META_OFF + mb * C::META_INTS * 4;
+            mbar_wait(meta_full + mb, (it / 3) & 1, 30);
+            const uint32_t info = ldsu(sm, meta + (TL_T + R + row) * 4);
             const uint32_t mask = info & 0xFFFFFFu;
             const int lo = -(int)(info >> 24);
             const int m = __popc(mask);
             const float wneg = (float)m * nratio;
-            for (int c = 0; c < NC; ++c)                                 // pass-A chunks go by without the epilogue
-                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+            const bool has_next = tile + (int)gridDim.x < ntiles;
+            if (it == 0)                                                 // the first tile's pass-A stage uses go by
+                for (int c = 0; c < NC; ++c)
+                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
             // every epilogue thread is done with the previous tile's coefficients before they are overwritten
             epi_bar();
-            if (etid < TL_CTX) asm volatile("st.shared.u32 [%0], %1;" ::"r"(maskT + etid * 4), "r"(0u) : "memory");
+            if (etid < TL_CTX) *reinterpret_cast<uint32_t*>(sm + C::MASK_OFF + etid * 4) = 0u;
             epi_bar();
             mbar_wait(s_full, it & 1, 31);
             tc_fence_after();
@@ -334,8 +341,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         if (on) {
                             const float g = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
                             const int cr = row + TL_HALO + off;          // context row of the pair, slot = win - off
-                            st_shared_f32(bandT + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
-                            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(maskT + cr * 4), "r"(1u << (win - off)) : "memory");
+                            sts1(sm, C::BAND_OFF + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
+                            atomicOr(reinterpret_cast<unsigned int*>(sm + C::MASK_OFF + cr * 4), 1u << (win - off));
                             if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
                         }
                         if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = f;
@@ -360,11 +367,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
                     for (int cq = 0; cq < 4; ++cq) {
                         const int c16 = (h & 1) * 4 + cq;                // 16-byte chunk of the 32-float block row
-                        st_shared_v4(gk_addr + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4),
-                                     g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                        const float4 gv = make_float4(g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                        sts4(sm, C::GK_OFF + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4), gv);
                         const int c32 = (c16 >> 1) ^ (row & 3);          // 32-byte chunk, 4-row period
-                        st_shared_v4(g32_addr + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16),
-                                     g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                        sts4(sm, C::G32_OFF + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16), gv);
                     }
                 }
             }
@@ -374,10 +380,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             epi_bar();                         // both groups read each other's coefficients below
 
             // ---- rows this thread updates in the chunks of its group
-            const int utok = (int)ld_shared_u32(meta + row * 4);
+            const int utok = (int)ldsu(sm, meta + row * 4);
             const bool u_on = m > 0;
             const float su = (a.row_scale0 != nullptr && u_on) ? __ldg(a.row_scale0 + utok) : 1.f;
-            const int ntok = row < NN ? (int)ld_shared_u32(meta + (TL_T + TL_CTX + row) * 4) : 0;
+            const int ntok = row < NN ? (int)ldsu(sm, meta + (TL_T + TL_CTX + row) * 4) : 0;
             const float sn = (a.row_scale1 != nullptr && row < NN) ? __ldg(a.row_scale1 + ntok) : 1.f;
             // context rows owned by this thread: `row` and, in warp 3 of the group, also row 128 + lane
             uint32_t cm[2]; int ctok[2]; float cs[2];
@@ -386,23 +392,25 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 const int rr = x == 0 ? row : ((q == 3) ? TL_T + lane : TL_CTX);
                 cm[x] = 0; ctok[x] = 0; cs[x] = 1.f;
                 if (rr < TL_CTX) {
-                    cm[x] = ld_shared_u32(maskT + rr * 4);
-                    ctok[x] = (int)ld_shared_u32(meta + (TL_T + rr) * 4);
+                    cm[x] = ldsu(sm, C::MASK_OFF + rr * 4);
+                    ctok[x] = (int)ldsu(sm, meta + (TL_T + rr) * 4);
                     if (a.row_scale1 != nullptr && cm[x]) cs[x] = __ldg(a.row_scale1 + ctok[x]);
                 }
             }
             // ---- pass B: accumulators + positive terms -> 16-byte atomics
             for (int c = 0; c < NC; ++c, ++gc) {
-                if ((int)(gc & 1) != grp) {                              // the other group's chunk
+                if ((int)(gc & 1) != grp) {                              // the other group's chunk (+ the next tile's pass-A use)
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                    if (has_next) { if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; } }
                     continue;
                 }
                 const int acc = gc & 1;
                 const int col0 = c * TL_BK;
-                const uint32_t stU = smem_u32(smStage + (size_t)stage * C::STAGE_BYTES);
+                const uint32_t stU = C::STAGE_OFF + stage * C::STAGE_BYTES;      // byte offsets from sm
                 const uint32_t stV = stU + TL_BLOCK_BYTES;
                 mbar_wait(full + stage, phase, 32);
-                // dV of one context row: sum over the centres ci = rr - 16 - win + k that have it as a context of g * u_ci
+                // dV of one context row: sum over the centres ci = rr - 16 - win + k that have it as a context of
+                // g * u_ci
                 auto band_dv = [&](int rr, uint32_t mm, float (&av)[32]) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) av[e] = 0.f;
@@ -410,41 +418,41 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         const int k = __ffs(mm) - 1;
                         mm &= mm - 1;
                         const int ci = rr - TL_HALO - win + k;
-                        const float g = ld_shared_f32(bandT + (uint32_t)(rr * TL_GB_STRIDE + k) * 4);
-                        const uint32_t ur = stU + (uint32_t)ci * 128;                // U row ci, SWIZZLE_128B_ATOM_32B
+                        const float g = lds1(sm, C::BAND_OFF + (uint32_t)(rr * TL_GB_STRIDE + k) * 4);
                         float4 xv[8];
 #pragma unroll
-                        for (int c32 = 0; c32 < 4; ++c32) {
-                            const uint32_t ph = ur + (uint32_t)((c32 ^ (ci & 3)) * 32);
-                            xv[2 * c32] = ld_shared_v4(ph); xv[2 * c32 + 1] = ld_shared_v4(ph + 16);
+                        for (int c32 = 0; c32 < 4; ++c32) {                          // U row ci, SWIZZLE_128B_ATOM_32B
+                            const uint32_t ph = stU + (uint32_t)ci * 128 + (uint32_t)((c32 ^ (ci & 3)) * 32);
+                            xv[2 * c32] = lds4(sm, ph); xv[2 * c32 + 1] = lds4(sm, ph + 16);
                         }
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            av[4 * e + 0] = fmaf(g, xv[e].x, av[4 * e + 0]); av[4 * e + 1] = fmaf(g, xv[e].y, av[4 * e + 1]);
-                            av[4 * e + 2] = fmaf(g, xv[e].z, av[4 * e + 2]); av[4 * e + 3] = fmaf(g, xv[e].w, av[4 * e + 3]);
-                        }
+                        for (int e = 0; e < 8; ++e) fma4(av, e, g, xv[e]);
                     }
                 };
                 // Row updates leave as COALESCED 16-byte atomics: the 32 rows of a warp are transposed through 4 KB of
                 // shared memory (the warp's quarter of this stage's U block, dead once its MMAs and the band reads are
                 // done) so that one RED instruction covers 4 rows x 128 contiguous bytes instead of 32 scattered
-                // 16-byte pieces -- the scattered form was measured LSU-bound (profiles/r2_tile_v2_ncu.md).
+                // 16-byte pieces -- the scattered form was measured LSU-bound (profiles/r2_tile_kernel.md).
                 const uint32_t scratch = stU + (uint32_t)q * 4096;
                 auto red_rows = [&](const float (&v)[32], float* mat, int tok, bool on, float scale) {
 #pragma unroll
                     for (int cq = 0; cq < 8; ++cq)
-                        st_shared_v4(scratch + (uint32_t)lane * 128 + (uint32_t)((cq ^ (lane & 7)) << 4), scale * v[4 * cq],
-                                     scale * v[4 * cq + 1], scale * v[4 * cq + 2], scale * v[4 * cq + 3]);
+                        sts4(sm, scratch + (uint32_t)lane * 128 + (uint32_t)((cq ^ (lane & 7)) << 4),
+                             make_float4(scale * v[4 * cq], scale * v[4 * cq + 1], scale * v[4 * cq + 2], scale * v[4 * cq + 3]));
                     __syncwarp();
                     const int tk = on ? tok : -1;
                     const int cq = lane & 7;
+                    float4 xr[8]; int rt[8];
 #pragma unroll
                     for (int ps = 0; ps < 8; ++ps) {
                         const int r = ps * 4 + (lane >> 3);
-                        const int rt = __shfl_sync(0xffffffffu, tk, r);
-                        const float4 x = ld_shared_v4(scratch + (uint32_t)r * 128 + (uint32_t)((cq ^ (r & 7)) << 4));
-                        if (rt >= 0 && col0 + 4 * cq < K && !(p.debug & 1))
-                            red_add_v4(mat + (size_t)rt * K + col0 + 4 * cq, x.x, x.y, x.z, x.w);
+                        rt[ps] = __shfl_sync(0xffffffffu, tk, r);
+                        xr[ps] = lds4(sm, scratch + (uint32_t)r * 128 + (uint32_t)((cq ^ (r & 7)) << 4));
+                    }
+                    if (col0 + 4 * cq < K && !(p.debug & 1)) {
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps)
+                            if (rt[ps] >= 0) red_add_v4(mat + (size_t)rt[ps] * K + col0 + 4 * cq, xr[ps]);
                     }
                     __syncwarp();
                 };
@@ -457,7 +465,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (col0 + 4 * j < K)
-                                red_add_v4(vrow + 4 * j, cs[1] * av[4 * j], cs[1] * av[4 * j + 1], cs[1] * av[4 * j + 2], cs[1] * av[4 * j + 3]);
+                                red_add_v4(vrow + 4 * j, make_float4(cs[1] * av[4 * j], cs[1] * av[4 * j + 1], cs[1] * av[4 * j + 2],
+                                                                     cs[1] * av[4 * j + 3]));
                     }
                 }
                 // (1b) context rows 0..127 into registers
@@ -483,16 +492,13 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         const int bit = __ffs(mm) - 1;
                         mm &= mm - 1;
                         const int j = row + TL_HALO + lo + bit;          // context row of this pair
-                        const float g = ld_shared_f32(bandT + (uint32_t)(j * TL_GB_STRIDE + win - lo - bit) * 4);
-                        const uint32_t vr = stV + (uint32_t)j * 128;     // V row j, SWIZZLE_128B
+                        const float g = lds1(sm, C::BAND_OFF + (uint32_t)(j * TL_GB_STRIDE + win - lo - bit) * 4);
                         float4 xv[8];
 #pragma unroll
-                        for (int cq = 0; cq < 8; ++cq) xv[cq] = ld_shared_v4(vr + (uint32_t)((cq ^ (j & 7)) << 4));
+                        for (int cq = 0; cq < 8; ++cq)                   // V row j, SWIZZLE_128B
+                            xv[cq] = lds4(sm, stV + (uint32_t)j * 128 + (uint32_t)((cq ^ (j & 7)) << 4));
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            au[4 * e + 0] = fmaf(g, xv[e].x, au[4 * e + 0]); au[4 * e + 1] = fmaf(g, xv[e].y, au[4 * e + 1]);
-                            au[4 * e + 2] = fmaf(g, xv[e].z, au[4 * e + 2]); au[4 * e + 3] = fmaf(g, xv[e].w, au[4 * e + 3]);
-                        }
+                        for (int e = 0; e < 8; ++e) fma4(au, e, g, xv[e]);
                     }
                     red_rows(au, p.syn0, utok, u_on, su);
                 }
@@ -511,6 +517,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 mbar_arrive(acc_empty + acc);
                 mbar_arrive(epi_done + stage);
                 if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                if (has_next) { if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; } }
             }
             mbar_arrive(tile_done + mb);
         }
