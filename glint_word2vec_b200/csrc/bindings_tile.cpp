@@ -55,7 +55,9 @@ void sgns_step_tile(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Ten
                     int64_t negatives, int64_t window_mode, double alpha, double max_grad, bool compute_loss,
                     int64_t grid, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs, Tensor tile_ws,
                     Tensor tile_negs, int64_t tile_negatives, c10::optional<Tensor> exp_table,
-                    c10::optional<Tensor> row_scale0, c10::optional<Tensor> row_scale1, c10::optional<Tensor> dbg) {
+                    c10::optional<Tensor> row_scale0, c10::optional<Tensor> row_scale1, c10::optional<Tensor> dbg,
+                    int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs,
+                    c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing) {
     TORCH_CHECK(syn0.is_cuda() && syn1.is_cuda() && syn0.is_contiguous() && syn1.is_contiguous(), "syn0/syn1: cuda contiguous");
     TORCH_CHECK(syn0.scalar_type() == torch::kFloat32 && syn1.scalar_type() == torch::kFloat32, "syn0/syn1 must be fp32");
     TORCH_CHECK(tokens.scalar_type() == torch::kInt32 && sent_id.scalar_type() == torch::kInt32 &&
@@ -93,7 +95,21 @@ void sgns_step_tile(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Ten
         p.exp_table = exp_table->data_ptr<float>();
     }
     p.debug = (int)debug;
-    p.world = 1; p.rank = 0;
+    p.world = (int)world; p.rank = (int)rank;
+    if (world > 1) {
+        // column shards: partial dot products are exchanged inside the kernel through peer-mapped symmetric memory
+        TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > ", gw2v::MAX_WORLD, " not supported");
+        TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
+        TORCH_CHECK(cta_seq.has_value() && error_flag.has_value(), "cta_seq / error_flag required");
+        TORCH_CHECK(cta_seq->scalar_type() == torch::kInt32 && cta_seq->numel() >= grid, "cta_seq");
+        for (int r = 0; r < world; ++r) {
+            p.xbuf[r] = reinterpret_cast<float*>(xbuf_ptrs[r]);
+            p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+        }
+        p.cta_seq = reinterpret_cast<uint32_t*>(cta_seq->data_ptr<int>());
+        p.error_flag = error_flag->data_ptr<int>();
+        p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
+    }
     auto opt_f = [&](c10::optional<Tensor>& t, int64_t n, const char* what) -> float* {
         if (!t.has_value()) return nullptr;
         TORCH_CHECK(t->is_cuda() && t->is_contiguous() && t->scalar_type() == torch::kFloat32 && t->numel() >= n, what);
@@ -127,4 +143,7 @@ void register_tile_bindings(py::module& m) {
     m.def("sgns_tile_supported", [](int64_t K, int64_t w, int64_t n, int64_t tc, int64_t tn) {
         return gw2v::sgns_tile_supported((int)K, (int)w, (int)n, (int)tc, (int)tn); });
     m.def("sgns_tile_max_tiles", [](int64_t t) { return (int64_t)gw2v::sgns_tile_max_tiles((int)t); });
+    m.def("sgns_tile_exchange_geometry", [](int64_t window, int64_t window_mode, int64_t tn) {
+        int slots, fl; gw2v::sgns_tile_exchange_geometry((int)window, (int)window_mode, (int)tn, &slots, &fl);
+        return std::vector<int64_t>{slots, fl}; });
 }

@@ -377,6 +377,93 @@ py::tuple encode_file(const std::string& path, const py::list& words, int64_t ma
     return py::make_tuple(a, o);
 }
 
+// Streaming variant of encode_file for corpora that must not be materialised in memory (the reference never holds
+// the corpus on one node either: RDD partitions, MLLIB:335-345).  The text file is processed in blocks of
+// `block_bytes` (cut at line boundaries); every block is encoded on all cores and appended to
+//   <out_prefix>.tokens.i32   (int32 token ids)        <out_prefix>.offsets.i64  (int64 sentence offsets, starts with 0)
+// Peak memory is one block of tokens, whatever the corpus size.  Returns (tokens, sentences).
+py::tuple encode_file_to(const std::string& path, const py::list& words, int64_t max_len, bool java_mode,
+                         int64_t num_threads, const std::string& out_prefix, int64_t block_bytes) {
+    std::string arena;
+    std::vector<std::pair<size_t, size_t>> spans;
+    spans.reserve((size_t)py::len(words));
+    for (py::handle w : words) {
+        Py_ssize_t len = 0;
+        const char* data = PyUnicode_AsUTF8AndSize(w.ptr(), &len);
+        if (!data) throw py::error_already_set();
+        spans.emplace_back(arena.size(), (size_t)len);
+        arena.append(data, (size_t)len);
+    }
+    size_t cap = 1 << 10;
+    while (cap < spans.size() * 2 + 2) cap <<= 1;
+    FlatStrMap idx(cap);
+    for (size_t i = 0; i < spans.size(); ++i) {
+        std::string_view w(arena.data() + spans[i].first, spans[i].second);
+        idx.find_or_insert(w, FlatStrMap::hash(w)).val = (int64_t)i;
+    }
+    int64_t ntok = 0, nsent = 0;
+    {
+        py::gil_scoped_release rel;
+        MappedFile f(path);
+        FILE* ft = fopen((out_prefix + ".tokens.i32").c_str(), "wb");
+        FILE* fo = fopen((out_prefix + ".offsets.i64").c_str(), "wb");
+        if (!ft || !fo) { if (ft) fclose(ft); if (fo) fclose(fo); throw std::runtime_error("cannot create " + out_prefix + ".*"); }
+        const int64_t zero = 0;
+        fwrite(&zero, sizeof(int64_t), 1, fo);
+        const size_t blk = (size_t)std::max<int64_t>(block_bytes, 1 << 20);
+        const unsigned nth = pick_threads(num_threads, f.size);
+        size_t begin = 0;
+        std::vector<int64_t> offs;
+        while (begin < f.size) {
+            size_t end = std::min(f.size, begin + blk);
+            while (end < f.size && f.data[end - 1] != '\n') ++end;
+            // thread chunks of this block, cut at line boundaries
+            std::vector<std::pair<size_t, size_t>> chunks;
+            size_t b = begin;
+            for (unsigned t = 0; t < nth && b < end; ++t) {
+                size_t e = (t + 1 == nth) ? end : std::max(b, begin + (end - begin) * (t + 1) / nth);
+                while (e < end && f.data[e - 1] != '\n') ++e;
+                if (e > b) chunks.emplace_back(b, e);
+                b = e;
+            }
+            std::vector<std::vector<int32_t>> toks(chunks.size());
+            std::vector<std::vector<int64_t>> lens(chunks.size());
+            auto work = [&](size_t t) {
+                auto& tk = toks[t];
+                auto& ln = lens[t];
+                for_lines(f.data + chunks[t].first, f.data + chunks[t].second, [&](const char* lb, const char* le) {
+                    int64_t in_chunk = 0;
+                    for_tokens(lb, le, java_mode, [&](std::string_view w) {
+                        const FlatStrMap::Slot* sl = idx.find(w, FlatStrMap::hash(w));
+                        if (!sl) return;
+                        if (in_chunk == max_len) { ln.push_back(in_chunk); in_chunk = 0; }
+                        tk.push_back((int32_t)sl->val);
+                        ++in_chunk;
+                    });
+                    if (in_chunk > 0) ln.push_back(in_chunk);
+                });
+            };
+            std::vector<std::thread> th;
+            for (size_t t = 1; t < chunks.size(); ++t) th.emplace_back(work, t);
+            if (!chunks.empty()) work(0);
+            for (auto& x : th) x.join();
+            for (size_t t = 0; t < chunks.size(); ++t) {
+                if (!toks[t].empty()) fwrite(toks[t].data(), sizeof(int32_t), toks[t].size(), ft);
+                offs.clear();
+                for (int64_t l : lens[t]) { ntok += l; offs.push_back(ntok); }
+                if (!offs.empty()) fwrite(offs.data(), sizeof(int64_t), offs.size(), fo);
+                nsent += (int64_t)lens[t].size();
+            }
+            madvise(const_cast<char*>(f.data + begin), end - begin, MADV_DONTNEED);      // drop the pages of the block
+            begin = end;
+        }
+        const bool ok = fclose(ft) == 0;
+        const bool ok2 = fclose(fo) == 0;
+        if (!ok || !ok2) throw std::runtime_error("write error on " + out_prefix + ".*");
+    }
+    return py::make_tuple(ntok, nsent);
+}
+
 py::tuple vose_alias(py::array_t<double, py::array::c_style | py::array::forcecast> p) {
     const int64_t v = (int64_t)p.size();
     const double* pp = p.data();
@@ -415,5 +502,7 @@ PYBIND11_MODULE(_host, m) {
     m.def("count_words_file", &count_words_file, py::arg("path"), py::arg("java_mode") = true, py::arg("num_threads") = 0);
     m.def("encode_file", &encode_file, py::arg("path"), py::arg("words"), py::arg("max_len"),
           py::arg("java_mode") = true, py::arg("num_threads") = 0);
+    m.def("encode_file_to", &encode_file_to, py::arg("path"), py::arg("words"), py::arg("max_len"), py::arg("java_mode") = true,
+          py::arg("num_threads") = 0, py::arg("out_prefix"), py::arg("block_bytes") = (int64_t)256 << 20);
     m.def("vose_alias", &vose_alias);
 }

@@ -55,6 +55,7 @@ constexpr int TL_ACC_STRIDE = 64;          // dUneg 32 | dVneg 32
 constexpr int TL_GB_STRIDE = 25;           // floats per row in the band-coefficient array (<= 23 slots + pad)
 constexpr int TL_BAND_BYTES = 17 * 1024;   // [160][25] coefficients by context row + [160] masks, padded to 1 KB
 constexpr int TL_MAXSTAGE = 4;
+constexpr int TL_XSLOTS = 4;               // exchange slots per CTA (>= 2 with the one-tile lead of the push)
 
 template <int R> struct TileCfg {
     static constexpr int NN = R - TL_CTX;                      // shared negatives per tile
@@ -107,12 +108,16 @@ __device__ __forceinline__ void fma4(float (&acc)[32], int e, float g, float4 x)
 
 }  // namespace
 
-template <int R>
+// SLP = 0: single shard.  SLP = 12 / 24: column shards -- band slots exchanged per centre (offsets -5..5 / -11..11)
+template <int R, int SLP>
 __global__ void __launch_bounds__(TL_THREADS, 1)
 sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm0s, const __grid_constant__ CUtensorMap tm1s, const TileArgs a) {
     using C = TileCfg<R>;
     constexpr int NN = C::NN;
+    constexpr bool MULTI = SLP > 0;
+    constexpr int WM = MULTI ? SLP / 2 - 1 : 0;                  // band slot s of the exchange payload <-> offset s - WM
+    constexpr int PAYF = SLP + NN;                               // exchanged floats per centre
     const SgnsParams& p = a.p;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1024-aligned, still a shared pointer
@@ -132,7 +137,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint64_t* acc_empty = bars + 16;  // [2] ... drained by the epilogue group that owns the buffer (128)
     uint64_t* meta_full = bars + 18;  // [3] tile meta loaded (three buffers: the producers run up to two tiles ahead)
     uint64_t* tile_done = bars + 21;  // [3] epilogue finished the tile (256): meta buffer reusable
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* b_full = bars + 24;     // [2] rows of the pass-B chunk that owns accumulator buffer x have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -152,7 +158,9 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             }
             mbar_init(s_full, 1);
             mbar_init(g_ready, TL_EPI_THREADS);
-            for (int x = 0; x < 2; ++x) { mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_GROUP_THREADS); }
+            for (int x = 0; x < 2; ++x) {
+                mbar_init(acc_full + x, 1); mbar_init(acc_empty + x, TL_GROUP_THREADS); mbar_init(b_full + x, 1);
+            }
             for (int x = 0; x < 3; ++x) { mbar_init(meta_full + x, 1); mbar_init(tile_done + x, TL_EPI_THREADS); }
             mbar_fence_init();
         }
@@ -169,7 +177,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         const int pw = warp - TL_PROD_WARP0;
         constexpr int MYG = C::NGROUPS / TL_NPROD;                   // gather4 copies of this warp per stage
         int stage = 0; uint32_t phase = 0;
-        uint32_t b_uses = 0;                                         // pass-B uses of each stage so far, 8 bits per stage
+        uint32_t b_par = 0;                                          // bit s: parity of the number of pass-B uses of stage s
         uint32_t last_b = 0;                                         // bit s: the current occupant of stage s is a pass-B chunk
         const int g = pw + TL_NPROD * lane;                          // this lane's gather4 copy; lanes [0, MYG) are active
         const bool is_u = g < TL_T / 4, is_ctx = !is_u && g < (TL_T + TL_CTX) / 4;
@@ -203,12 +211,12 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         };
         auto fill = [&](const CUtensorMap* tm, const int4& ids, int c, bool pass_b) {
             mbar_wait(empty + stage, phase ^ 1, 11);
-            if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, ((b_uses >> (8 * stage)) - 1) & 1, 12);
+            if ((last_b >> stage) & 1u) mbar_wait(epi_done + stage, ((b_par >> stage) & 1u) ^ 1u, 12);
             uint8_t* st = sm + C::STAGE_OFF + stage * C::STAGE_BYTES;
             if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(MYG * 512));
             __syncwarp();
             if (lane < MYG) tma_gather4(st + g * 512, tm, c * TL_BK, ids.x, ids.y, ids.z, ids.w, full + stage);
-            if (pass_b) { last_b |= 1u << stage; b_uses += 1u << (8 * stage); } else { last_b &= ~(1u << stage); }
+            if (pass_b) { last_b |= 1u << stage; b_par ^= 1u << stage; } else { last_b &= ~(1u << stage); }
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
         };
         // Ring order: A(first tile), then per tile t: B(t, 0), A(t+1, 0), B(t, 1), A(t+1, 1), ... -- the S GEMM of the
@@ -263,6 +271,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             for (int c = 0; c < NC; ++c, ++gc) {
                 const int acc = gc & 1;
                 mbar_wait(full + stage, phase, 22);
+                if (lane == 0) mbar_arrive(b_full + acc);               // the chunk's rows have landed: its epilogue group may read them
                 mbar_wait(acc_empty + acc, ((gc >> 1) & 1) ^ 1, 23);
                 tc_fence_after();
                 if (elect_one()) {
@@ -306,6 +315,75 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         uint32_t gc = 0;
+        const uint32_t seq0 = MULTI ? p.cta_seq[blockIdx.x] : 0u;       // tile sequence of this CTA, persists across launches
+        // Column shards, phase-A epilogue of tile iteration `pit` (one group, thread = centre): the used entries of the
+        // partial S -- SLP band slots + NN negatives per centre -- go from TMEM straight into every rank's exchange slot
+        // (st.global on peer-mapped addresses over NVLink), then ONE release per destination publishes the tile.
+        auto exchange_push = [&](int pit, int bar_id) {
+            if constexpr (MULTI) {
+                mbar_wait(s_full, pit & 1, 34);
+                tc_fence_after();
+                const uint32_t tag = seq0 + (uint32_t)pit + 1u;
+                const uint32_t slot = (seq0 + (uint32_t)pit) % TL_XSLOTS;
+                const size_t slot_base = ((size_t)blockIdx.x * TL_XSLOTS + slot) * (size_t)p.world;
+                const bool loop = (p.debug & 8) != 0;                    // single-GPU loopback of the protocol (tests, ncu)
+                const float sc = loop ? 1.f / (float)p.world : 1.f;      // loopback: every "rank" contributes 1/S of the dots
+                auto push4 = [&](int f0, float4 v) {
+                    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                    for (int r = 0; r < p.world; ++r) {
+                        const int src = loop ? r : p.rank;
+                        float* dst = p.xbuf[r] + ((slot_base + src) * TL_T + (size_t)row) * PAYF + f0;
+                        asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    }
+                };
+                {   // band: column 16 + lane + off of the window [32q, 32q + 64) for off = s - WM
+                    float xw[64];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        uint32_t x[16];
+                        tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xw[16 * h + j] = __uint_as_float(x[j]);
+                    }
+#pragma unroll
+                    for (int s4 = 0; s4 < SLP / 4; ++s4) {
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c0 = TL_HALO + 4 * s4 + e - WM;    // column for lane 0; lane l reads c0 + l
+                            float t = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (c0 + k >= 0 && c0 + k < 64) t = (lane == k) ? xw[c0 + k] : t;
+                            v[e] = t;
+                        }
+                        push4(4 * s4, make_float4(v[0], v[1], v[2], v[3]));
+                    }
+                }
+#pragma unroll 1
+                for (int h = 0; h < NN / 16; ++h) {
+                    uint32_t x[16];
+                    tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        push4(SLP + 16 * h + 4 * j4, make_float4(__uint_as_float(x[4 * j4]), __uint_as_float(x[4 * j4 + 1]),
+                                                                 __uint_as_float(x[4 * j4 + 2]), __uint_as_float(x[4 * j4 + 3])));
+                }
+                tc_fence_before();
+                // all 128 payload rows are written (by other threads): barrier, then one release per destination
+                if (bar_id == 2) asm volatile("bar.sync 2, %0;" ::"n"(TL_GROUP_THREADS) : "memory");
+                else asm volatile("bar.sync 3, %0;" ::"n"(TL_GROUP_THREADS) : "memory");
+                if (row < p.world) {
+                    const int src = loop ? row : p.rank;
+                    __threadfence_system();
+                    st_release_sys(p.flags[row] + slot_base + src, tag);
+                }
+            }
+        };
+        if (MULTI && (int)blockIdx.x < ntiles && grp == 0) exchange_push(0, 2);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int mb = it % 3;
             const uint32_t meta = C::META_OFF + mb * C::META_INTS * 4;
@@ -323,54 +401,120 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             epi_bar();
             if (etid < TL_CTX) *reinterpret_cast<uint32_t*>(sm + C::MASK_OFF + etid * 4) = 0u;
             epi_bar();
-            mbar_wait(s_full, it & 1, 31);
-            tc_fence_after();
-            if (grp == 0) {
-                // ---- band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
-#pragma unroll 1
-                for (int h = 0; h < 4; ++h) {
-                    uint32_t x[16];
-                    tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
-                    tmem_ld_wait();
+            // one (centre, context) candidate: coefficient into bandT / maskT
+            auto band_emit = [&](int off, float f) {
+                const int bit = off - lo;
+                if (bit >= 0 && bit < 24 && ((mask >> bit) & 1u)) {
+                    const float g = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
+                    const int cr = row + TL_HALO + off;                  // context row of the pair, slot = win - off
+                    sts1(sm, C::BAND_OFF + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
+                    atomicOr(reinterpret_cast<unsigned int*>(sm + C::MASK_OFF + cr * 4), 1u << (win - off));
+                    if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                }
+            };
+            // 16 (centre, shared negative) dots: coefficients into Gneg in both operand layouts
+            auto negs_emit = [&](int h, const float (&f)[16]) {
+                float g[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int off = 16 * h + j - TL_HALO - lane;     // context offset of this column for this centre
-                        const int bit = off - lo;
-                        const bool on = bit >= 0 && bit < 24 && ((mask >> bit) & 1u);
-                        const float f = __uint_as_float(x[j]);
-                        if (on) {
-                            const float g = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
-                            const int cr = row + TL_HALO + off;          // context row of the pair, slot = win - off
-                            sts1(sm, C::BAND_OFF + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
-                            atomicOr(reinterpret_cast<unsigned int*>(sm + C::MASK_OFF + cr * 4), 1u << (win - off));
-                            if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                for (int j = 0; j < 16; ++j) {
+                    g[j] = m > 0 ? wneg * sgns_coeff(f[j], 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
+                    if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f[j]); maxdot = fmaxf(maxdot, fabsf(f[j])); }
+                }
+                const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int c16 = (h & 1) * 4 + cq;                    // 16-byte chunk of the 32-float block row
+                    const float4 gv = make_float4(g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
+                    sts4(sm, C::GK_OFF + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4), gv);
+                    const int c32 = (c16 >> 1) ^ (row & 3);              // 32-byte chunk, 4-row period
+                    sts4(sm, C::G32_OFF + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16), gv);
+                }
+            };
+            if constexpr (!MULTI) {
+                mbar_wait(s_full, it & 1, 31);
+                tc_fence_after();
+                if (grp == 0) {
+                    // band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
+#pragma unroll 1
+                    for (int h = 0; h < 4; ++h) {
+                        uint32_t x[16];
+                        tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            band_emit(16 * h + j - TL_HALO - lane, __uint_as_float(x[j]));
+                            if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = __uint_as_float(x[j]);
                         }
-                        if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = f;
+                    }
+                } else {
+                    // shared negatives: columns [160, 160 + NN)
+#pragma unroll 1
+                    for (int h = 0; h < NN / 16; ++h) {
+                        uint32_t x[16];
+                        tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
+                        tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[j] = __uint_as_float(x[j]);
+                            if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + TL_CTX + 16 * h + j] = f[j];
+                        }
+                        negs_emit(h, f);
                     }
                 }
             } else {
-                // ---- shared negatives: columns [160, 160 + NN) -> Gneg in both operand layouts
-#pragma unroll 1
-                for (int h = 0; h < NN / 16; ++h) {
-                    uint32_t x[16];
-                    tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
-                    tmem_ld_wait();
-                    float g[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float f = __uint_as_float(x[j]);
-                        g[j] = m > 0 ? wneg * sgns_coeff(f, 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
-                        if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f); maxdot = fmaxf(maxdot, fabsf(f)); }
-                        if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + TL_CTX + 16 * h + j] = f;
+                // ---- column shards: the partial dots of this tile were pushed by every rank (exchange_push below, one
+                // tile ago); wait for all of them, sum in rank order (bit-identical coefficients on every rank: the
+                // reference's coefficient broadcast disappears, MLLIB:423-425) and continue as on a single shard
+                const uint32_t tag = seq0 + (uint32_t)it + 1u;
+                const uint32_t slot = (seq0 + (uint32_t)it) % TL_XSLOTS;
+                const size_t slot_base = ((size_t)blockIdx.x * TL_XSLOTS + slot) * (size_t)p.world;
+                if (etid < p.world) {
+                    const uint32_t* fl = p.flags[p.rank] + slot_base + etid;
+                    const unsigned long long t0 = tc_globaltimer_ns();
+                    while (ld_acquire_sys(fl) != tag) {
+                        if (tc_globaltimer_ns() - t0 > 10000000000ull) {
+                            printf("[gw2v] tile exchange: rank %d cta %d timed out waiting for rank %d (tag %u)\n", p.rank,
+                                   (int)blockIdx.x, etid, tag);
+                            atomicExch(p.error_flag, 1);
+                            __trap();
+                        }
                     }
-                    const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
+                    if (p.timing != nullptr) atomicAdd(p.timing, tc_globaltimer_ns() - t0);
+                }
+                epi_bar();
+                const float* xin = p.xbuf[p.rank] + (slot_base * TL_T + (size_t)row) * PAYF;      // + src * 128 * PAYF
+                auto ld_sys = [](const float* ptr) {
+                    float4 v;
+                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+                    return v;
+                };
+                if (grp == 0) {
 #pragma unroll
-                    for (int cq = 0; cq < 4; ++cq) {
-                        const int c16 = (h & 1) * 4 + cq;                // 16-byte chunk of the 32-float block row
-                        const float4 gv = make_float4(g[4 * cq], g[4 * cq + 1], g[4 * cq + 2], g[4 * cq + 3]);
-                        sts4(sm, C::GK_OFF + rowoff + (uint32_t)((c16 ^ (row & 7)) << 4), gv);
-                        const int c32 = (c16 >> 1) ^ (row & 3);          // 32-byte chunk, 4-row period
-                        sts4(sm, C::G32_OFF + rowoff + (uint32_t)(c32 * 32 + (c16 & 1) * 16), gv);
+                    for (int s4 = 0; s4 < SLP / 4; ++s4) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int src = 0; src < p.world; ++src) {
+                            const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + 4 * s4);
+                            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+                        }
+                        band_emit(4 * s4 + 0 - WM, t.x); band_emit(4 * s4 + 1 - WM, t.y);
+                        band_emit(4 * s4 + 2 - WM, t.z); band_emit(4 * s4 + 3 - WM, t.w);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int h = 0; h < NN / 16; ++h) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+                        for (int src = 0; src < p.world; ++src) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + SLP + 16 * h + 4 * j4);
+                                f[4 * j4] += v.x; f[4 * j4 + 1] += v.y; f[4 * j4 + 2] += v.z; f[4 * j4 + 3] += v.w;
+                            }
+                        }
+                        negs_emit(h, f);
                     }
                 }
             }
@@ -408,7 +552,11 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 const int col0 = c * TL_BK;
                 const uint32_t stU = C::STAGE_OFF + stage * C::STAGE_BYTES;      // byte offsets from sm
                 const uint32_t stV = stU + TL_BLOCK_BYTES;
-                mbar_wait(full + stage, phase, 32);
+                // The stage's own `full` barrier cannot be used here: a group only handles every other chunk, so it would
+                // skip phases of that barrier and a parity wait that skips a phase can pass early (seen with the odd ring of
+                // NN = 64: stale U rows).  The MMA warp observes every stage use in order and forwards "landed" on a
+                // barrier that belongs to the accumulator buffer, i.e. to this group alone.
+                mbar_wait(b_full + acc, (gc >> 1) & 1, 32);
                 // dV of one context row: sum over the centres ci = rr - 16 - win + k that have it as a context of
                 // g * u_ci
                 auto band_dv = [&](int rr, uint32_t mm, float (&av)[32]) {
@@ -519,8 +667,12 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
                 if (has_next) { if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; } }
             }
+            // column shards: the group that did not own the last chunk pushes the next tile's partial dots while the other
+            // group is still busy with its updates -- the NVLink latency hides behind the tail of pass B
+            if (MULTI && has_next && grp == (int)(gc & 1)) exchange_push(it + 1, 2 + grp);
             mbar_arrive(tile_done + mb);
         }
+        if (MULTI && blockIdx.x < gridDim.x && etid == 0) p.cta_seq[blockIdx.x] = seq0 + (uint32_t)it;
         if (p.compute_loss) {
             loss = warp_sum(loss);
             maxdot = warp_max(maxdot);
@@ -562,7 +714,7 @@ bool sgns_tile_supported(int K, int window, int negatives, int tile_centres, int
 
 int sgns_tile_max_tiles(int max_tokens) { return (max_tokens + TL_T - 1) / TL_T; }
 
-template <int R>
+template <int R, int SLP>
 static int launch_tile_r(const SgnsParams& p, const TileLaunch& l, cudaStream_t stream) {
     using C = TileCfg<R>;
     CUtensorMap tm0, tm1, tm0s, tm1s;
@@ -575,22 +727,40 @@ static int launch_tile_r(const SgnsParams& p, const TileLaunch& l, cudaStream_t 
     a.p = p;
     a.cinfo = l.cinfo; a.tile_negs = l.tile_negs; a.n_pairs = l.n_pairs;
     a.row_scale0 = l.row_scale0; a.row_scale1 = l.row_scale1; a.dbg = l.dbg;
-    auto kern = sgns_tile_kernel<R>;
+    auto kern = sgns_tile_kernel<R, SLP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     kern<<<l.grid, TL_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tm0s, tm1s, a);
     return 0;
 }
 
+// band slots exchanged per centre over column shards: offsets -5..5 (12 floats) or -11..11 (24 floats)
+int sgns_tile_band_slots(int window, int window_mode) {
+    const int win = window_mode == 0 ? window - 1 : window;
+    return win <= 5 ? 12 : 24;
+}
+
+void sgns_tile_exchange_geometry(int window, int window_mode, int tile_negatives, int* slots, int* floats_per_slot_src) {
+    *slots = TL_XSLOTS;
+    *floats_per_slot_src = TL_T * (sgns_tile_band_slots(window, window_mode) + tile_negatives);
+}
+
 int launch_sgns_tile(const SgnsParams& p, const TileLaunch& l, cudaStream_t stream) {
     if (l.max_tokens <= 0) return 0;
     const int nn = l.tile_negatives;
+    if (nn != 32 && nn != 64) return 1;
     const int max_tiles = sgns_tile_max_tiles(l.max_tokens);
     const int total = max_tiles * (nn / 2);
     tile_negs_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p.n_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi, p.iteration,
                                                               p.pos0, nn, l.tile_negs);
-    if (nn == 32) return launch_tile_r<192>(p, l, stream);
-    if (nn == 64) return launch_tile_r<224>(p, l, stream);
-    return 1;
+    const int slp = p.world > 1 ? sgns_tile_band_slots(p.window, p.window_mode) : 0;
+    if (nn == 32) {
+        if (slp == 0) return launch_tile_r<192, 0>(p, l, stream);
+        if (slp == 12) return launch_tile_r<192, 12>(p, l, stream);
+        return launch_tile_r<192, 24>(p, l, stream);
+    }
+    if (slp == 0) return launch_tile_r<224, 0>(p, l, stream);
+    if (slp == 12) return launch_tile_r<224, 12>(p, l, stream);
+    return launch_tile_r<224, 24>(p, l, stream);
 }
 
 }  // namespace gw2v

@@ -20,6 +20,8 @@ struct TileLaunch {
 
 bool sgns_tile_supported(int K, int window, int negatives, int tile_centres, int tile_negatives);
 int sgns_tile_max_tiles(int max_tokens);
+// column shards: exchange ring geometry (slots per CTA, floats per (slot, source rank))
+void sgns_tile_exchange_geometry(int window, int window_mode, int tile_negatives, int* slots, int* floats_per_slot_src);
 // pair_count + scan must have run on the same stream (launch_paircount); returns 0, 1 = unsupported, 2 = tensor map
 int launch_sgns_tile(const SgnsParams& p, const TileLaunch& l, cudaStream_t stream);
 

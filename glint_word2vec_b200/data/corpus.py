@@ -31,9 +31,34 @@ def java_split(line: str, sep: str = " ") -> List[str]:
 
 @dataclass
 class EncodedCorpus:
-    """Flat int32 token stream plus sentence offsets (CSR)."""
+    """Flat int32 token stream plus sentence offsets (CSR).
+
+    The arrays may be ``np.memmap`` views of ``<prefix>.tokens.i32`` / ``<prefix>.offsets.i64`` (``open`` /
+    ``save``): a corpus that does not fit in host memory is then streamed from disk step by step, and a shard-server
+    group receives the PREFIX instead of the tokens (every rank maps the same files; the reference likewise never
+    materialises the corpus on one node: RDD partitions, MLLIB:335-345)."""
     tokens: np.ndarray          # int32 [N]
     offsets: np.ndarray         # int64 [num_sentences + 1]
+    prefix: str | None = None   # set when the arrays are disk-backed
+
+    @classmethod
+    def open(cls, prefix: str) -> "EncodedCorpus":
+        import os
+        tp, op = prefix + ".tokens.i32", prefix + ".offsets.i64"
+        ntok = os.path.getsize(tp) // 4
+        toks = np.memmap(tp, dtype=np.int32, mode="r", shape=(ntok,)) if ntok else np.zeros(0, np.int32)
+        offs = np.memmap(op, dtype=np.int64, mode="r", shape=(os.path.getsize(op) // 8,))
+        return cls(toks, offs, prefix)
+
+    def save(self, prefix: str, chunk: int = 1 << 24) -> "EncodedCorpus":
+        """Write the arrays to ``<prefix>.*`` in chunks and return the disk-backed twin."""
+        with open(prefix + ".tokens.i32", "wb") as f:
+            for lo in range(0, self.num_tokens, chunk):
+                f.write(np.ascontiguousarray(self.tokens[lo:lo + chunk], dtype=np.int32).tobytes())
+        with open(prefix + ".offsets.i64", "wb") as f:
+            for lo in range(0, self.offsets.shape[0], chunk):
+                f.write(np.ascontiguousarray(self.offsets[lo:lo + chunk], dtype=np.int64).tobytes())
+        return EncodedCorpus.open(prefix)
 
     @property
     def num_tokens(self) -> int:
@@ -94,11 +119,22 @@ def iter_text_file(path: str, tokenizer: str = "java") -> Iterator[List[str]]:
 
 
 def encode_text_file(path: str, vocab: Vocabulary, max_sentence_length: int = 1000, tokenizer: str = "java",
-                     use_native: bool = True, num_threads: int = 0) -> EncodedCorpus:
+                     use_native: bool = True, num_threads: int = 0, out_prefix: str | None = None,
+                     block_bytes: int = 256 << 20) -> EncodedCorpus:
     """Text file -> encoded corpus (OOV dropped, sentences chunked, MLLIB:335-343) without materialising Python
-    token lists: ``csrc/host/textproc.cpp::encode_file`` mmaps the file and encodes on all cores."""
+    token lists: ``csrc/host/textproc.cpp::encode_file`` mmaps the file and encodes on all cores.
+
+    ``out_prefix``: stream the result to ``<out_prefix>.tokens.i32`` / ``.offsets.i64`` block by block
+    (``encode_file_to``) and return a memory-mapped corpus -- peak host memory is one block, whatever the file size."""
     if tokenizer not in ("java", "whitespace"):
         raise ValueError(f"unknown tokenizer {tokenizer!r}")
+    if out_prefix is not None:
+        from ..ops import host as _host
+        if use_native and _host.available():
+            _host.encode_file_to(path, list(vocab.words), int(max_sentence_length), tokenizer == "java", num_threads,
+                                 out_prefix, block_bytes)
+            return EncodedCorpus.open(out_prefix)
+        return encode_corpus(iter_text_file(path, tokenizer), vocab, max_sentence_length, use_native=False).save(out_prefix)
     if use_native:
         from ..ops import host as _host
         if _host.available():
@@ -132,7 +168,7 @@ def iter_steps(corpus: EncodedCorpus, step_tokens: int) -> Iterator[StepBatch]:
         e = int(np.searchsorted(offs, start + step_tokens, side="right")) - 1
         if e <= s:                       # a single sentence larger than the step
             end = min(int(offs[s + 1]), start + step_tokens)
-            toks = corpus.tokens[start:end]
+            toks = np.ascontiguousarray(corpus.tokens[start:end])
             sid = np.zeros(end - start, dtype=np.int32)
             yield StepBatch(toks, sid, start, end - start)
             if end == int(offs[s + 1]):
@@ -142,7 +178,7 @@ def iter_steps(corpus: EncodedCorpus, step_tokens: int) -> Iterator[StepBatch]:
                 offs[s] = end
             continue
         end = int(offs[e])
-        toks = corpus.tokens[start:end]
+        toks = np.ascontiguousarray(corpus.tokens[start:end])      # memmap slice -> one sequential read of the step
         lens = np.diff(offs[s:e + 1])
         sid = np.repeat(np.arange(e - s, dtype=np.int32), lens)
         yield StepBatch(toks, sid, start, end - start)

@@ -238,6 +238,34 @@ class CudaShardOps:
         }
         self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
 
+    def _setup_tile_exchange(self):
+        """Symmetric exchange ring of the tensor-core tile kernel (collective): per CTA ``slots`` x ``world`` payloads of
+        128 centres x (band slots + tile negatives) partial dots, plus one release flag per (CTA, slot, source rank)."""
+        from ..parallel.symm import SymmBuffer, alloc_symmetric
+        cfg = self.cfg
+        grid = self._tile_grid
+        slots, fl = [int(v) for v in _C.sgns_tile_exchange_geometry(cfg.window, WINDOW_MODES[cfg.window_mode],
+                                                                    cfg.tile_negatives)]
+        xbytes = (grid * slots * self.world * fl * 4 + 255) // 256 * 256
+        fbytes = (grid * slots * self.world * 4 + 255) // 256 * 256
+        if self._loopback > 1:
+            local = torch.zeros(xbytes + fbytes, dtype=torch.uint8, device=self.dev)
+            buf = SymmBuffer(local, [local.data_ptr()] * self.world, 0, None)
+        else:
+            # every rank must run the identical persistent grid: CTA c of rank a exchanges with CTA c of rank b
+            g = torch.tensor([grid, -grid], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(g, op=dist.ReduceOp.MIN, group=self.e.comm.group)
+            if int(g[0].item()) != grid or int(-g[1].item()) != grid:
+                raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
+            buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
+        self._xchg = {
+            "buf": buf, "grid": grid, "variant": "tile",
+            "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
+            "cta_seq": torch.zeros(grid, dtype=torch.int32, device=self.dev),
+            "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
+        }
+        self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
+
     def _want_nvls(self) -> bool:
         """multimem.st push: transport="nvls" (or GW2V_NVLS=1) and a multicast mapping granted by the driver."""
         env = os.environ.get("GW2V_NVLS")
@@ -333,21 +361,24 @@ class CudaShardOps:
             tok, sid = tok_dev, sid_dev
         self._stats_i = (self._stats_i + 1) % self._stats_ring.shape[0]
         stats = self._stats_ring[self._stats_i]
-        pairs_path = (self.world > 1 and self._xchg["variant"] == 3) or \
-            (self.world == 1 and getattr(self, "_variant", None) == 3)
+        pairs_path = (not self._tile_mode) and ((self.world > 1 and self._xchg["variant"] == 3) or
+                                                (self.world == 1 and getattr(self, "_variant", None) == 3))
         if not pairs_path and not self._tile_mode:
             stats.zero_()                 # the pairs path zeroes them inside pair_tile_scan_kernel (one launch less)
         wm = WINDOW_MODES[cfg.window_mode]
         if self._tile_mode:
-            if self.world > 1:
-                raise NotImplementedError('neg_sharing="tile" over column shards')
             if not hasattr(self, "_tile_grid"):
                 self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
+            if self.world > 1 and self._xchg is None:
+                self._setup_tile_exchange()
+            x = self._xchg if self.world > 1 else None
             _C.sgns_step_tile(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
                               int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                               float(cfg.max_grad), self.compute_loss, self._tile_grid, self.debug, self.pg_cinfo,
                               self.pg_off, self.pg_npairs, self.pg_tiles, self.tile_negs, cfg.tile_negatives,
-                              self.exp_table, self.row_scale0, self.row_scale1, self.tile_dbg)
+                              self.exp_table, self.row_scale0, self.row_scale1, self.tile_dbg,
+                              self.world, self.rank, x["xptrs"] if x else [], x["fptrs"] if x else [],
+                              x["cta_seq"] if x else None, x["err"] if x else None, self.timing if x else None)
             self.launches += 4            # pair_count, pair_tile_scan, tile_negs, sgns_tile
             return stats
         if self.world > 1 and self._xchg["variant"] == 3:

@@ -62,3 +62,13 @@ def encode_file(path: str, words, max_sentence_length: int, java_mode: bool = Tr
     m = _load()
     toks, offs = m.encode_file(str(path), list(words), int(max_sentence_length), bool(java_mode), int(num_threads))
     return np.asarray(toks, dtype=np.int32), np.asarray(offs, dtype=np.int64)
+
+
+def encode_file_to(path: str, words, max_sentence_length: int, java_mode: bool, num_threads: int, out_prefix: str,
+                   block_bytes: int = 256 << 20):
+    """Streaming ``encode_file``: appends to ``<out_prefix>.tokens.i32`` / ``.offsets.i64`` block by block; returns
+    (tokens, sentences)."""
+    m = _load()
+    ntok, nsent = m.encode_file_to(str(path), list(words), int(max_sentence_length), bool(java_mode), int(num_threads),
+                                   str(out_prefix), int(block_bytes))
+    return int(ntok), int(nsent)

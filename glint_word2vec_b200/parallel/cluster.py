@@ -31,7 +31,7 @@ import sys
 import tempfile
 import time
 import uuid
-from multiprocessing.connection import Client as _ConnClient
+import socket
 from typing import Optional, Tuple
 
 import numpy as np
@@ -42,6 +42,7 @@ from ..models import matrix_io, trainer
 from ..models.engine import EngineOptions, ShardEngine
 from ..models.sgns import SGNSConfig
 from . import server as _server
+from . import wire
 from .comm import Comm, comm_from_env
 
 
@@ -157,33 +158,41 @@ class RemoteHandle(MatrixHandle):
     one Glint cluster)."""
 
     def __init__(self, host: str, port: int, matrix_id: Optional[str] = None, owned_procs=None,
-                 persist_host: str = ""):
+                 persist_host: str = "", secret: Optional[bytes] = None, scratch_dir: Optional[str] = None):
         self.addr = (host, port)
         self.matrix_id = matrix_id or uuid.uuid4().hex[:12]
         self._procs = owned_procs or []
         self.host = persist_host
+        self._secret = secret if secret is not None else wire.load_secret()
+        if self._secret is None:
+            raise PermissionError("no server secret: set GW2V_SERVER_SECRET (or GW2V_SERVER_SECRET_FILE) to the secret "
+                                  "of the shard-server group")
+        self._scratch = scratch_dir
         info = self._call("info")
         self.num_shards = info["world"]
         self.device = info["device"]
         self.last_report: Optional[dict] = None
 
-    # -- transport
+    # -- transport: JSON header + raw numpy buffers over an HMAC-authenticated socket (parallel/wire.py)
     def _call(self, op, *args, timeout: float = 300.0, **kwargs):
         deadline = time.time() + 30.0
         while True:
             try:
-                conn = _ConnClient(self.addr, authkey=_server.AUTHKEY)
+                conn = socket.create_connection(self.addr, timeout=30.0)
                 break
             except (ConnectionRefusedError, OSError):
                 if time.time() > deadline:
                     raise
                 time.sleep(0.1)
         try:
-            conn.send({"op": op, "args": args, "kwargs": kwargs})
+            wire.client_handshake(conn, self._secret)
+            wire.send_msg(conn, {"op": op, "args": list(args), "kwargs": kwargs})
             # the reference awaits RPCs with 1-5 minute time-outs (MLLIB:429,486,497)
-            if not conn.poll(timeout):
-                raise TimeoutError(f"server did not answer {op!r} within {timeout}s")
-            resp = conn.recv()
+            conn.settimeout(timeout)
+            try:
+                resp = wire.recv_msg(conn)
+            except socket.timeout:
+                raise TimeoutError(f"server did not answer {op!r} within {timeout}s") from None
         finally:
             conn.close()
         if not resp["ok"]:
@@ -202,8 +211,19 @@ class RemoteHandle(MatrixHandle):
         return r
 
     def fit(self, corpus, lr, iters, train_words, metrics_path=None, train_opts=None):
-        self.last_report = self._call("fit", self.matrix_id, corpus.tokens, corpus.offsets, lr, iters,
-                                      train_words, metrics_path, train_opts, timeout=7 * 24 * 3600.0)
+        """The corpus goes to the shards as a PATH: a disk-backed corpus is used as is, an in-memory one is written
+        once to a scratch prefix; every rank memory-maps the same files (nothing is pickled or re-broadcast)."""
+        tmp = None
+        if corpus.prefix is None:
+            tmp = tempfile.mkdtemp(prefix="gw2v_corpus_", dir=self._scratch)
+            corpus = corpus.save(os.path.join(tmp, "corpus"))
+        try:
+            self.last_report = self._call("fit", self.matrix_id, {"prefix": corpus.prefix}, lr, iters, train_words,
+                                          metrics_path, train_opts, timeout=7 * 24 * 3600.0)
+        finally:
+            if tmp is not None:
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
         return self.last_report
 
     def pull(self, rows):
@@ -220,7 +240,8 @@ class RemoteHandle(MatrixHandle):
         return self._call("multiply", self.matrix_id, np.asarray(q, np.float32))
 
     def top_k(self, queries, k):
-        return self._call("top_k", self.matrix_id, np.asarray(queries, np.float32), int(k))
+        idx, sim = self._call("top_k", self.matrix_id, np.asarray(queries, np.float32), int(k))
+        return idx, sim
 
     def save(self, path, extra=None):
         return self._call("save", self.matrix_id, path, extra, timeout=3600.0)
@@ -275,7 +296,11 @@ def spawn_integrated(num_servers: int, device_type: str, options: Optional[dict]
             proc.kill()
             raise TimeoutError("shard-server group did not come up")
         time.sleep(0.1)
-    return RemoteHandle("127.0.0.1", port, owned_procs=[proc], persist_host="")
+    with open(ready) as f:
+        info = json.load(f)
+    # the group generated its own secret and wrote it into the 0600 ready-file: only this user can reach it
+    secret = info["secret"].encode() if info.get("secret") else wire.load_secret(options)
+    return RemoteHandle("127.0.0.1", port, owned_procs=[proc], persist_host="", secret=secret, scratch_dir=tmp)
 
 
 def connect_separate(host: str) -> RemoteHandle:

@@ -29,7 +29,7 @@ import socket
 import sys
 import time
 import traceback
-from multiprocessing.connection import Listener
+import select
 from typing import Dict, Optional
 
 import numpy as np
@@ -40,12 +40,18 @@ from ..data.corpus import EncodedCorpus
 from ..models import matrix_io
 from ..models.engine import EngineOptions, ShardEngine
 from ..models.sgns import SGNSConfig
+from . import wire
 from .comm import Comm, TorchDistComm, init_process_group
 
 log = logging.getLogger("glint_word2vec_b200.server")
 
 DEFAULT_PORT = 13370           # cf. glint.master.port 13380 in separate-glint.conf (SEPCONF:3)
-AUTHKEY = b"glint-word2vec-b200"
+HEARTBEAT_S = 20.0             # rank 0 broadcasts an idle beat at least this often, so collectives can time out
+COLLECTIVE_TIMEOUT_S = 900.0   # a rank that waits longer than this inside a control collective gives up (group dies)
+# the wire protocol: nothing else can be invoked, whatever the client sends
+ALLOWED_OPS = frozenset({"info", "create", "fit", "pull", "pull_average", "norms", "multiply", "top_k", "save", "load",
+                         "set_noise", "destroy"})
+MUTATING_OPS = frozenset({"create", "fit", "load", "set_noise"})
 
 
 def parse_host(host: str, default_port: int = DEFAULT_PORT):
@@ -69,6 +75,10 @@ class ShardServer:
         self.comm = comm
         self.device = device
         self.default_options = dict(default_options or {})
+        # when set, every path a client names (save / load / corpus / metrics / checkpoints) must resolve below it
+        self.data_root = self.default_options.pop("data_root", None)
+        for k in ("secret", "secret_file", "port", "bind"):
+            self.default_options.pop(k, None)
         self.engines: Dict[str, ShardEngine] = {}
         self.reports: Dict[str, dict] = {}
 
@@ -77,6 +87,19 @@ class ShardServer:
         merged = dict(self.default_options)
         merged.update(opts or {})
         return EngineOptions.from_dict(merged)
+
+    def _path(self, path: Optional[str]) -> Optional[str]:
+        """Validate a client-supplied filesystem path against ``data_root``."""
+        if path is None:
+            return None
+        if not isinstance(path, str) or "\x00" in path:
+            raise ValueError("bad path")
+        if self.data_root:
+            root = os.path.realpath(self.data_root)
+            real = os.path.realpath(path)
+            if real != root and not real.startswith(root + os.sep):
+                raise PermissionError(f"path {path!r} is outside the server's data_root")
+        return path
 
     def _eng(self, mid: str) -> ShardEngine:
         if mid not in self.engines:
@@ -95,11 +118,20 @@ class ShardServer:
         self.engines[mid] = eng
         return {"cols": eng.cfg.vector_size, "shards": self.comm.world}
 
-    def op_fit(self, mid, tokens, offsets, lr, iters, train_words, metrics_path=None, train_opts=None):
+    def op_fit(self, mid, corpus, lr, iters, train_words, metrics_path=None, train_opts=None):
+        """``corpus``: ``{"prefix": p}`` -- every rank memory-maps ``p.tokens.i32`` / ``p.offsets.i64`` (the corpus
+        never travels through the control plane, cf. RDD partitions MLLIB:335-345) -- or ``{"tokens": .., "offsets": ..}``
+        for small in-memory corpora."""
         from .cluster import run_training
         eng = self._eng(mid)
-        corpus = EncodedCorpus(np.asarray(tokens, np.int32), np.asarray(offsets, np.int64))
-        rep = run_training(eng, corpus, lr, iters, train_words, metrics_path, train_opts)
+        if "prefix" in corpus:
+            enc = EncodedCorpus.open(self._path(corpus["prefix"]))
+        else:
+            enc = EncodedCorpus(np.asarray(corpus["tokens"], np.int32), np.asarray(corpus["offsets"], np.int64))
+        train_opts = dict(train_opts or {})
+        if train_opts.get("checkpoint_dir"):
+            self._path(train_opts["checkpoint_dir"])
+        rep = run_training(eng, enc, float(lr), int(iters), int(train_words), self._path(metrics_path), train_opts)
         out = {k: getattr(rep, k) for k in ("iterations", "steps", "words", "pairs", "loss_per_pair",
                                              "max_abs_dot", "seconds", "final_alpha")}
         out["history"] = rep.history[-50:]
@@ -124,11 +156,11 @@ class ShardServer:
         return idx.numpy(), sim.numpy()
 
     def op_save(self, mid, path, extra=None):
-        matrix_io.save_matrix(self._eng(mid), path, extra)
+        matrix_io.save_matrix(self._eng(mid), self._path(path), extra)
         return True
 
     def op_load(self, mid, path, opts=None, with_syn1=True):
-        eng = matrix_io.load_matrix(path, self.comm, self.device, self._opts(opts), with_syn1)
+        eng = matrix_io.load_matrix(self._path(path), self.comm, self.device, self._opts(opts), with_syn1)
         self.engines[mid] = eng
         return {"cols": eng.cfg.vector_size, "shards": self.comm.world,
                 "vocab_size": eng.cfg.vocab_size, "config": eng.cfg.to_dict()}
@@ -144,79 +176,140 @@ class ShardServer:
         return True
 
     def execute(self, req: dict):
-        fn = getattr(self, "op_" + req["op"], None)
-        if fn is None:
-            raise ValueError(f"unknown op {req['op']!r}")
-        return fn(*req.get("args", ()), **req.get("kwargs", {}))
+        op = req.get("op")
+        if op not in ALLOWED_OPS:
+            raise ValueError(f"unknown op {op!r}")
+        args, kwargs = req.get("args", []), req.get("kwargs", {})
+        if not isinstance(args, (list, tuple)) or not isinstance(kwargs, dict):
+            raise ValueError("malformed request")
+        # fault injection for the tests of the agreement step: fail `op` on one rank only
+        if os.environ.get("GW2V_TEST_FAIL_OP") == op and os.environ.get("GW2V_TEST_FAIL_RANK") == str(self.comm.rank):
+            raise RuntimeError("injected failure")
+        return getattr(self, "op_" + op)(*args, **kwargs)
 
 
 def _bcast_request(comm: Comm, req):
-    """Rank 0 -> all ranks.  numpy payloads ride as pickled objects on the Gloo
-    control group (cold path; the hot path never leaves the device)."""
+    """Rank 0 -> all ranks on the Gloo control group.  The object was decoded from the safe wire format on rank 0
+    (plain dict / list / numpy), so what the ranks exchange among themselves is only ever data this group built."""
     if comm.world == 1:
         return req
     return comm.broadcast_object(req, src=0)
 
 
-def serve(comm: Comm, device: torch.device, port: int, bind: str = "0.0.0.0",
+def _is_loopback(bind: str) -> bool:
+    return bind in ("127.0.0.1", "localhost", "::1")
+
+
+def serve(comm: Comm, device: torch.device, port: int, bind: str = "127.0.0.1",
           options: Optional[dict] = None, ready_file: Optional[str] = None):
     """Run the request loop until a ``shutdown`` request arrives."""
+    configured = wire.load_secret(options)
     server = ShardServer(comm, device, options)
-    listener = None
+    srv = None
+    secret = configured
     if comm.rank == 0:
-        listener = Listener((bind, port), authkey=AUTHKEY)
-        ip = _local_ip()
+        if secret is None:
+            if not _is_loopback(bind):
+                raise SystemExit("refusing to listen on %s without a configured secret: set GW2V_SERVER_SECRET, or "
+                                 "`secret` / `secret_file` in the server config" % bind)
+            secret = wire.new_secret()          # private to whoever can read the 0600 ready-file (the spawning client)
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((bind, port))
+        srv.listen(32)
+        ip = "127.0.0.1" if _is_loopback(bind) else _local_ip()
         # the reference prints the master IP to the log for the user to copy (README.md:56)
         print(f"master = {ip}:{port}", flush=True)
         if ready_file:
-            with open(ready_file, "w") as f:
-                json.dump({"host": ip, "port": port, "pid": os.getpid(), "world": comm.world}, f)
+            fd = os.open(ready_file + ".tmp", os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+            with os.fdopen(fd, "w") as f:
+                json.dump({"host": ip, "port": port, "pid": os.getpid(), "world": comm.world,
+                           "secret": None if configured else secret.decode()}, f)
+            os.replace(ready_file + ".tmp", ready_file)
+    conn = None
     running = True
     while running:
-        conn = None
+        req = None
         if comm.rank == 0:
+            req = {"op": "_idle"}
             try:
-                conn = listener.accept()
-            except Exception as e:  # bad auth etc.
-                log.warning("rejected connection: %s", e)
-                continue
-        while True:
-            req = None
-            if comm.rank == 0:
-                try:
-                    req = conn.recv()
-                except (EOFError, ConnectionError, OSError):
-                    req = {"op": "_disconnect"}
-            req = _bcast_request(comm, req)
-            if req["op"] == "_disconnect":
-                break
-            if req["op"] == "shutdown":
-                running = False
-                if comm.rank == 0:
-                    try:
-                        conn.send({"ok": True, "result": True})
-                    except Exception:
-                        pass
-                break
+                if conn is None:
+                    r, _, _ = select.select([srv], [], [], HEARTBEAT_S)
+                    if r:
+                        c, _addr = srv.accept()
+                        try:
+                            c.settimeout(30.0)
+                            wire.server_handshake(c, secret)
+                            c.settimeout(None)
+                            conn = c
+                        except Exception as e:
+                            log.warning("rejected connection: %s", e)
+                            c.close()
+                if conn is not None:
+                    r, _, _ = select.select([conn], [], [], HEARTBEAT_S)
+                    if r:
+                        conn.settimeout(600.0)
+                        msg = wire.recv_msg(conn)
+                        conn.settimeout(None)
+                        if not isinstance(msg, dict) or not isinstance(msg.get("op"), str):
+                            raise wire.WireError("malformed request")
+                        req = msg
+            except (EOFError, ConnectionError, OSError, wire.WireError, ValueError) as e:
+                if not isinstance(e, EOFError):
+                    log.warning("dropping connection: %s", e)
+                if conn is not None:
+                    conn.close()
+                    conn = None
+        req = _bcast_request(comm, req)
+        op = req["op"]
+        if op == "_idle":                       # heartbeat: keeps every rank inside short-lived collectives only
+            continue
+        if op == "shutdown":
+            running = False
+            resp = {"ok": True, "result": True}
+        else:
             try:
                 result = server.execute(req)
                 resp = {"ok": True, "result": result}
             except Exception as e:
                 resp = {"ok": False, "error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()}
-            if comm.rank == 0:
-                try:
-                    conn.send(resp)
-                except (ConnectionError, OSError):
-                    pass
-        if conn is not None:
+            resp = _agree(comm, server, req, resp)
+        if comm.rank == 0 and conn is not None:
             try:
+                wire.send_msg(conn, resp)
+            except (ConnectionError, OSError, wire.WireError) as e:
+                log.warning("could not answer %s: %s", op, e)
                 conn.close()
-            except Exception:
-                pass
-    if listener is not None:
-        listener.close()
+                conn = None
+    if conn is not None:
+        conn.close()
+    if srv is not None:
+        srv.close()
     for mid in list(server.engines):
         server.op_destroy(mid)
+
+
+def _agree(comm: Comm, server: "ShardServer", req: dict, resp: dict) -> dict:
+    """Every rank reports whether its handler succeeded; if they disagree (a shard file unreadable on one rank, an
+    OOM on one GPU, ...) the request fails on ALL ranks, and a matrix that a mutating op left half-built is dropped
+    everywhere so that the group stays consistent and keeps serving."""
+    if comm.world == 1:
+        return resp
+    status = comm.gather_objects((bool(resp["ok"]), resp.get("error")), dst=0)
+    verdict = None
+    if comm.rank == 0:
+        bad = [(r, err) for r, (ok, err) in enumerate(status) if not ok]
+        verdict = {"bad": [[r, err] for r, err in bad], "mixed": 0 < len(bad) < comm.world}
+    verdict = comm.broadcast_object(verdict, src=0)
+    if verdict["bad"]:
+        args = req.get("args") or [None]
+        if req.get("op") in MUTATING_OPS and isinstance(args[0], str) and (verdict["mixed"] or req["op"] != "fit"):
+            server.op_destroy(args[0])
+        if resp["ok"] or verdict["mixed"]:
+            ranks = ", ".join(f"rank {r}: {err}" for r, err in verdict["bad"])
+            resp = {"ok": False, "error": f"request {req.get('op')!r} failed on {len(verdict['bad'])} of {comm.world} "
+                                           f"shards ({ranks})", "trace": resp.get("trace", "")}
+    return resp
 
 
 def _local_ip() -> str:
@@ -231,7 +324,7 @@ def _local_ip() -> str:
 
 
 def rank_main(rank: int, world: int, port: int, master_port: int, device_type: str,
-              options: Optional[dict], ready_file: Optional[str], bind: str = "0.0.0.0"):
+              options: Optional[dict], ready_file: Optional[str], bind: str = "127.0.0.1"):
     """Entry point of one server rank (one process per GPU)."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(master_port)
@@ -246,9 +339,10 @@ def rank_main(rank: int, world: int, port: int, master_port: int, device_type: s
         torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
     comm: Comm
     if world > 1:
-        # ranks idle inside a collective while rank 0 waits for client requests: no short time-out here
+        # rank 0 sends an idle beat every HEARTBEAT_S, so no rank ever waits long inside a control collective unless a
+        # peer is stuck or dead: then the collective times out, the rank exits and the group monitor stops the group
         init_process_group(rank=rank, world=world, master_port=master_port, device=device,
-                           timeout_s=30 * 24 * 3600.0)
+                           timeout_s=float((options or {}).get("collective_timeout_s", COLLECTIVE_TIMEOUT_S)))
         comm = TorchDistComm()
     else:
         comm = Comm()
@@ -266,7 +360,9 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="stand-alone shard-server group (cf. glint.Main)")
     ap.add_argument("--num-servers", "-n", type=int, default=0, help="column shards (0 = all GPUs, or 1 on CPU)")
     ap.add_argument("--port", type=int, default=DEFAULT_PORT)
-    ap.add_argument("--bind", default="0.0.0.0")
+    ap.add_argument("--bind", default="127.0.0.1",
+                    help="listen address; anything but loopback requires a configured secret (GW2V_SERVER_SECRET, "
+                         "or `secret` / `secret_file` in the -c config)")
     ap.add_argument("--device", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("-c", "--config", default=None, help="JSON file with engine options (cf. `-c separate-glint.conf`)")
     ap.add_argument("--ready-file", default=None)

@@ -25,6 +25,9 @@ case "${1:-}" in
     if running; then echo "already running: $(cat "$STATE/master")"; exit 0; fi
     n="${2:-2}"
     rm -f "$STATE/ready"
+    # per-deployment secret shared by the group and its clients (parallel/wire.py); 0600
+    ( umask 077; head -c 32 /dev/urandom | od -An -tx1 | tr -d ' \n' > "$STATE/secret" )
+    export GW2V_SERVER_SECRET_FILE="$STATE/secret"
     ( cd "$ROOT" && exec setsid "$PY" -m glint_word2vec_b200.parallel.server --num-servers "$n" --port "$PORT" \
         --bind 127.0.0.1 -c "${GW2V_IT_CONF:-$ROOT/configs/it-separate-server.json}" --device "${GW2V_IT_DEVICE:-cpu}" --ready-file "$STATE/ready" \
         > "$STATE/server.log" 2>&1 ) &
@@ -44,7 +47,7 @@ case "${1:-}" in
   exec)
     shift
     running || { echo "environment is not running (scripts/it_env.sh start)" >&2; exit 1; }
-    GW2V_IT_SERVER_HOST="$(cat "$STATE/master")" "$@"
+    GW2V_SERVER_SECRET_FILE="$STATE/secret" GW2V_IT_SERVER_HOST="$(cat "$STATE/master")" "$@"
     ;;
   stop)
     if running; then

@@ -49,6 +49,8 @@ def separate_cluster(tmp_path_factory):
     conf = str(tmp / "separate.json")
     with open(conf, "w") as f:
         json.dump({"subsample_mode": "reference"}, f)                  # cf. separate-glint.conf (SEPCONF)
+    # a separate group is reached with a per-deployment secret shared by server and clients (parallel/wire.py)
+    os.environ["GW2V_SERVER_SECRET"] = "it-" + os.urandom(8).hex()
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     proc = subprocess.Popen([sys.executable, "-m", "glint_word2vec_b200.parallel.server", "--num-servers", "2",
                              "--port", str(port), "--bind", "127.0.0.1", "--device", "cpu", "-c", conf,

@@ -115,3 +115,74 @@ def test_fused_multi_matches_oracle(world, d, nvls, serve_fused, debug, tmp_path
     assert torch.allclose(r["sim16"], want_sim, atol=2e-5)
     assert (r["idx16"] == want_idx).float().mean() > 0.98          # ties / last-place swaps only
     assert r["idx16"][:, 0].tolist() == list(range(100, 116))
+
+
+def _worker_tile(rank, world, port, d, nn, out_dir):
+    import torch.distributed as dist
+    from glint_word2vec_b200.data.sampler import zipf_counts
+    from glint_word2vec_b200.models import sgns
+    from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+    from glint_word2vec_b200.models.sgns import SGNSConfig
+    from glint_word2vec_b200.parallel.comm import TorchDistComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        v = 200000
+        cfg = SGNSConfig(v, d, 5, 5, seed=11, neg_sharing="tile", tile_negatives=nn)
+        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference"))
+        eng.init_weights()
+        eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
+        full1 = (torch.rand(v, eng.shard.padded_vector_size, generator=torch.Generator().manual_seed(5)) - 0.5) * 0.5
+        full1[:, d:] = 0
+        eng.syn1 = full1[:, rank * eng.shard.cols:(rank + 1) * eng.shard.cols].contiguous().to(dev)
+        eng.syn0 = (eng.syn0 * 20.0).contiguous()
+        rng = np.random.default_rng(3)
+        steps = []
+        for t in (5000, 128 * 148 + 77, 300):
+            tokens = rng.choice(v, size=t, replace=False).astype(np.int32)
+            steps.append((tokens, (np.arange(t) // 41).astype(np.int32)))
+        start0 = eng.pull(torch.arange(v)).cpu()
+        stats, pos = [], 0
+        for tokens, sid in steps:
+            stats.append(eng.train_step(tokens, sid, pos, 0, 0.02).cpu())
+            pos += len(tokens)
+        torch.cuda.synchronize(dev)
+        got0 = eng.pull(torch.arange(v)).cpu()
+        err = int(eng._cuda._xchg["err"].item())
+        if rank == 0:
+            ref0, _ = sgns.init_embeddings(v, d, 11)
+            ref0 = ref0 * 20.0
+            ref1 = full1[:, :d].clone()
+            pairs, losses, pos = [], [], 0
+            for tokens, sid in steps:
+                st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, pos, 0, 0.02)
+                pairs.append(st.pairs)
+                losses.append(st.loss)
+                pos += len(tokens)
+            torch.save({"got0": got0, "ref0": ref0, "start0": start0, "pairs": pairs, "losses": losses,
+                        "stats": torch.stack(stats), "err": err}, os.path.join(out_dir, "result_tile.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d,nn", [(2, 128, 32), (2, 100, 64), (4, 256, 32), (8, 512, 32), (8, 512, 64)])
+def test_tile_kernel_column_shards_match_oracle(world, d, nn, tmp_path):
+    """neg_sharing="tile" over column shards: the tcgen05 kernel with the in-kernel NVLink exchange of the partial
+    S entries (csrc/sgns_tile.cu) against the dense single-process oracle."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_tile, args=(world, _free_port(), d, nn, str(tmp_path)), nprocs=world, join=True)
+    r = torch.load(os.path.join(tmp_path, "result_tile.pt"))
+    assert r["err"] == 0
+    assert [int(x) for x in r["stats"][:, 0]] == r["pairs"]
+    for got, want in zip(r["stats"][:, 1].tolist(), r["losses"]):
+        assert abs(got - want) / want < 5e-3
+    upd_ref = r["ref0"] - r["start0"]
+    upd_got = r["got0"] - r["start0"]
+    assert upd_ref.norm() > 0
+    assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2

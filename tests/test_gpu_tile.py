@@ -158,3 +158,32 @@ def test_tile_kernel_sentence_boundaries_and_steps():
     r0, r1 = ref0 - syn0[:, :d], ref1 - syn1[:, :d]
     assert float((got0 - syn0[:, :d] - r0).norm() / r0.norm()) < 3e-2
     assert float((got1 - syn1[:, :d] - r1).norm() / r1.norm()) < 3e-2
+
+
+@pytest.mark.parametrize("world,d,nn,wmode,window", [(2, 64, 32, "reference", 5), (8, 128, 64, "reference", 5),
+                                                     (4, 100, 32, "word2vec_c", 7)])
+def test_tile_kernel_exchange_protocol_loopback(world, d, nn, wmode, window, monkeypatch):
+    """The column-shard protocol of the tile kernel (payload extraction from TMEM, slots, release/acquire flags, ordered
+    sum, one-tile lead of the push) on ONE GPU: with GW2V_LOOPBACK_WORLD = S every push lands in the GPU's own
+    exchange buffer as the message of "rank" r carrying 1/S of the dots, so the result must equal the single-shard
+    oracle.  Several steps: the slot ring and the sequence numbers carry over from launch to launch."""
+    dev = _dev()
+    monkeypatch.setenv("GW2V_LOOPBACK_WORLD", str(world))
+    v = 200000
+    eng, syn0, syn1 = _engine(dev, v, d, nn, window=window, wmode=wmode)
+    rng = np.random.default_rng(4)
+    ref0, ref1 = syn0[:, :d].clone(), syn1[:, :d].clone()
+    pos = 0
+    for t in (700, 128 * 148 * 2 + 5, 100, 3000):
+        tokens = rng.choice(v, size=t, replace=False).astype(np.int32)
+        sid = (np.arange(t) // 29).astype(np.int32)
+        st = sgns.sgns_minibatch_reference(ref0, ref1, eng.cfg, eng.alias, tokens, sid, pos, 0, 0.002)
+        stats = eng.train_step(tokens, sid, pos, 0, 0.002).cpu()
+        assert int(stats[0]) == st.pairs
+        assert abs(float(stats[1]) - st.loss) / st.loss < 5e-3
+        pos += t
+    got0, got1 = eng.syn0.cpu()[:, :d], eng.syn1.cpu()[:, :d]
+    r0, r1 = ref0 - syn0[:, :d], ref1 - syn1[:, :d]
+    assert float((got0 - syn0[:, :d] - r0).norm() / r0.norm()) < 3e-2
+    assert float((got1 - syn1[:, :d] - r1).norm() / r1.norm()) < 3e-2
+    assert int(eng._cuda._xchg["err"].item()) == 0
