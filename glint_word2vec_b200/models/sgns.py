@@ -217,10 +217,19 @@ class StepStats:
     max_abs_dot: float = 0.0
 
 
+def _scaled_index_add(mat: torch.Tensor, idx: torch.Tensor, upd: torch.Tensor, scale: Optional[torch.Tensor]):
+    """``mat[idx] += scale[idx] * upd`` -- ``scale`` is the optional per-row update scale (hot-row damping)."""
+    if scale is not None:
+        upd = upd * scale[idx].to(upd.dtype)[:, None]
+    mat.index_add_(0, idx, upd)
+
+
 def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSConfig,
                              alias: AliasTable, tokens: np.ndarray, sent_id: np.ndarray,
                              pos0: int, iteration: int, alpha: float,
-                             lo: int = 0, hi: Optional[int] = None) -> StepStats:
+                             lo: int = 0, hi: Optional[int] = None,
+                             row_scale0: Optional[torch.Tensor] = None,
+                             row_scale1: Optional[torch.Tensor] = None) -> StepStats:
     """One mini-batch (centres ``lo..hi`` of the step) applied in place.
 
     All dots use pre-update rows; all updates are summed (index_add), i.e. the
@@ -233,7 +242,8 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
     if ci.shape[0] == 0:
         return stats                      # zero-pair batches are a clean no-op (Q4)
     if cfg.neg_sharing == "tile":
-        return _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats)
+        return _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
+                                         row_scale0, row_scale1)
     pos = np.uint64(pos0) + ci.astype(np.uint64)
     neg = draw_negatives(cfg, alias, pos, slot, iteration)
     tok = tokens.astype(np.int64)
@@ -253,13 +263,14 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
     du = gplus[:, None] * vc + torch.einsum("pn,pnd->pd", gminus, vn)
     dvc = gplus[:, None] * u
     dvn = gminus[:, :, None] * u[:, None, :]
-    syn0.index_add_(0, w, du)
-    syn1.index_add_(0, c, dvc)
-    syn1.index_add_(0, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]))
+    _scaled_index_add(syn0, w, du, row_scale0)
+    _scaled_index_add(syn1, c, dvc, row_scale1)
+    _scaled_index_add(syn1, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]), row_scale1)
     return stats
 
 
-def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats) -> StepStats:
+def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
+                              row_scale0=None, row_scale1=None) -> StepStats:
     """neg_sharing="tile": positives per pair, negatives per (active centre, shared negative of its tile) with
     weight m_i * n / N; every dot from pre-update rows, all updates summed."""
     tok = tokens.astype(np.int64)
@@ -285,10 +296,10 @@ def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, a
     dvc = gplus[:, None] * u
     du_neg = torch.einsum("an,and->ad", gminus, vn)
     dvn = gminus[:, :, None] * ua[:, None, :]
-    syn0.index_add_(0, w, du_pos)
-    syn0.index_add_(0, wa, du_neg)
-    syn1.index_add_(0, c, dvc)
-    syn1.index_add_(0, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]))
+    _scaled_index_add(syn0, w, du_pos, row_scale0)
+    _scaled_index_add(syn0, wa, du_neg, row_scale0)
+    _scaled_index_add(syn1, c, dvc, row_scale1)
+    _scaled_index_add(syn1, ng.reshape(-1), dvn.reshape(-1, dvn.shape[-1]), row_scale1)
     return stats
 
 

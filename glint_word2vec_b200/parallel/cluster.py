@@ -55,17 +55,21 @@ def run_training(engine, corpus, lr, iters, train_words, metrics_path=None, trai
         import json
         with open(os.path.join(checkpoint.latest(ckdir), "state.json")) as f:
             st = json.load(f)
+        fp = checkpoint.fingerprint(engine, corpus)
+        checkpoint.check_fingerprint(st, fp)                  # a stale directory of another run is an error, not a resume
         engine.opts.step_tokens = int(st["step_tokens"])
         from ..models import matrix_io as _mio
         loaded = _mio.load_matrix(checkpoint.latest(ckdir), engine.comm, engine.device, engine.opts)
         engine.syn0, engine.syn1 = loaded.syn0, loaded.syn1
         ck = checkpoint.Checkpointer(engine, ckdir, every, {k: st[k] for k in (
-            "learning_rate", "num_iterations", "train_words", "step_tokens")}) if every > 0 else None
+            "learning_rate", "num_iterations", "train_words", "step_tokens")}, fp=fp,
+            run_id=st.get("run_id")) if every > 0 else None
         return trainer.train(engine, corpus, st["learning_rate"], st["num_iterations"], st["train_words"],
                              metrics_path=metrics_path, checkpoint_fn=ck, start_iteration=st["iteration"],
                              start_step=st["next_step"])
     if ckdir and every > 0:
-        return checkpoint.train_with_checkpoints(engine, corpus, lr, iters, train_words, ckdir, every, metrics_path)
+        return checkpoint.train_with_checkpoints(engine, corpus, lr, iters, train_words, ckdir, every, metrics_path,
+                                                 overwrite=bool(o.get("checkpoint_overwrite", False)))
     return trainer.train(engine, corpus, lr, iters, train_words, metrics_path=metrics_path)
 
 

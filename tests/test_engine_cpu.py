@@ -397,3 +397,47 @@ def test_streamed_matrix_io_round_trip_in_small_chunks(tmp_path, monkeypatch):
     assert raw.shape == (v, d) and np.array_equal(raw, e.syn0[:, :d].numpy())
     back = matrix_io.load_matrix(str(tmp_path / "m"), Comm(), torch.device("cpu"))
     assert torch.equal(back.syn0, e.syn0) and torch.equal(back.syn1, e.syn1)
+
+
+def test_checkpoint_pruning_never_deletes_latest_and_stale_runs_are_refused(tmp_path):
+    """pruning sorted every ckpt-* by name, so in a directory holding an older run's ckpt-0002-* the
+    checkpoint just written was deleted right after LATEST was pointed at it; and resume=true picked up a finished
+    run's state.  Now: only own checkpoints are pruned, never LATEST; a fresh run refuses a used directory; resume
+    checks a corpus / configuration fingerprint."""
+    from glint_word2vec_b200.data.corpus import EncodedCorpus
+    from glint_word2vec_b200.models import checkpoint
+    from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+    from glint_word2vec_b200.models.sgns import SGNSConfig
+    rng = np.random.default_rng(0)
+    v = 200
+
+    def make(seed=3):
+        eng = ShardEngine(SGNSConfig(v, 16, seed=seed), device=torch.device("cpu"),
+                          options=EngineOptions(subsample_mode="reference", step_tokens=500))
+        eng.init_weights()
+        eng.set_noise(np.arange(v, 0, -1))
+        return eng
+    toks = rng.integers(0, v, size=4000).astype(np.int32)
+    corpus = EncodedCorpus(toks, np.arange(0, 4001, 40, dtype=np.int64))
+    d = str(tmp_path / "ck")
+    os.makedirs(os.path.join(d, "ckpt-0002-00000009", "matrix"))                  # leftovers of an earlier run
+    eng = make()
+    hyper = dict(learning_rate=0.05, num_iterations=1, train_words=4000, step_tokens=500)
+    ck = checkpoint.Checkpointer(eng, d, 1, hyper, keep=2, fp=checkpoint.fingerprint(eng, corpus))
+    for step in (1, 2, 3, 4):
+        ck.save(0, step)
+        assert checkpoint.latest(d) == os.path.join(d, f"ckpt-0000-{step:08d}")   # the newest one always survives
+    left = sorted(x for x in os.listdir(d) if x.startswith("ckpt-"))
+    assert left == ["ckpt-0000-00000003", "ckpt-0000-00000004", "ckpt-0002-00000009"]      # foreign directory untouched
+    # a fresh run refuses the used directory ...
+    with pytest.raises(FileExistsError):
+        checkpoint.train_with_checkpoints(make(), corpus, 0.05, 1, 4000, d, 2)
+    # ... unless told to overwrite it
+    checkpoint.train_with_checkpoints(make(), corpus, 0.05, 1, 4000, d, 2, overwrite=True)
+    assert "ckpt-0002-00000009" not in os.listdir(d) and checkpoint.latest(d) is not None
+    # resume with another corpus (or seed) is an error, not a silent continuation of somebody else's run
+    other = EncodedCorpus(rng.integers(0, v, size=4000).astype(np.int32), corpus.offsets)
+    from glint_word2vec_b200.parallel.comm import Comm
+    with pytest.raises(ValueError, match="does not belong to this run"):
+        checkpoint.resume(d, other, np.arange(v, 0, -1), Comm(), torch.device("cpu"),
+                          EngineOptions(subsample_mode="reference"))

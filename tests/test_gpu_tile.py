@@ -187,3 +187,28 @@ def test_tile_kernel_exchange_protocol_loopback(world, d, nn, wmode, window, mon
     assert float((got0 - syn0[:, :d] - r0).norm() / r0.norm()) < 3e-2
     assert float((got1 - syn1[:, :d] - r1).norm() / r1.norm()) < 3e-2
     assert int(eng._cuda._xchg["err"].item()) == 0
+
+
+@pytest.mark.parametrize("d,nn,grid", [(128, 64, 4), (128, 32, 3), (300, 64, 2), (64, 32, 1)])
+def test_tile_kernel_many_tiles_per_cta(d, nn, grid, monkeypatch):
+    """Few CTAs, many tiles each (what a 131 072-token step does on 148 SMs): the stage ring interleaves pass B of tile
+    t with pass A of tile t+1, and with the 3-stage ring of NN = 64 a stage alternates between the two kinds.  A parity
+    wait that skipped a phase once let an epilogue group read stale U rows here (fixed: per-accumulator `b_full`)."""
+    dev = _dev()
+    monkeypatch.setenv("GW2V_TILE_GRID", str(grid))
+    v = 200000
+    eng, syn0, syn1 = _engine(dev, v, d, nn)
+    rng = np.random.default_rng(8)
+    ref0, ref1 = syn0[:, :d].clone(), syn1[:, :d].clone()
+    pos = 0
+    for t in (3000, 1500):
+        tokens = rng.choice(v, size=t, replace=False).astype(np.int32)
+        sid = (np.arange(t) // 33).astype(np.int32)
+        st = sgns.sgns_minibatch_reference(ref0, ref1, eng.cfg, eng.alias, tokens, sid, pos, 0, 0.002)
+        stats = eng.train_step(tokens, sid, pos, 0, 0.002).cpu()
+        assert int(stats[0]) == st.pairs
+        pos += t
+    got0, got1 = eng.syn0.cpu()[:, :d], eng.syn1.cpu()[:, :d]
+    r0, r1 = ref0 - syn0[:, :d], ref1 - syn1[:, :d]
+    assert float((got0 - syn0[:, :d] - r0).norm() / r0.norm()) < 2e-2
+    assert float((got1 - syn1[:, :d] - r1).norm() / r1.norm()) < 2e-2
