@@ -17,7 +17,7 @@ def one(world, d, nn, t, grid=0, steps=1):
     dev = torch.device("cuda", 0)
     v = 200000
     cfg = SGNSConfig(v, d, 5, 5, seed=7, neg_sharing="tile", tile_negatives=nn)
-    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
     eng.init_weights(); eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
     g = torch.Generator().manual_seed(0)
     syn1 = torch.randn(v, eng.shard.cols, generator=g) * (0.5 / d ** 0.5)

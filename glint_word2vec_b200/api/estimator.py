@@ -29,7 +29,7 @@ JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
 _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "kernel",
                 "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                "tile_negatives", "device")
+                "tile_negatives", "device", "hot_row_cap", "sampler")
 
 
 def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:
@@ -39,6 +39,10 @@ def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:
     opts = {k: v for k, v in cfg.items() if k in _ENGINE_KEYS}
     opts["batch_size"] = p.getBatchSize()
     opts["subsample_ratio"] = p.getSubsampleRatio()
+    # numPartitions = asynchronous workers of the reference (MLLIB:122-126,345,392): the staleness knob of the engine;
+    # unigramTableSize is honoured by sampler="table" (MLLIB:239-244)
+    opts["num_partitions"] = p.getNumPartitions()
+    opts["unigram_table_size"] = p.getUnigramTableSize()
     return opts
 
 
@@ -58,7 +62,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
     process is one rank of a torchrun job, in-process for one shard, else spawn
     an integrated shard-server group."""
     engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                                                        "tile_negatives", "device")}
+                                                        "tile_negatives", "device", "hot_row_cap", "sampler")}
     if host:
         h = _cluster.connect_separate(host)
         return h.create(cfg, engine_opts, counts)
@@ -78,7 +82,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
 
 def open_handle_for_load(path: str, host: str, num_servers: int, opts: dict):
     engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                                                        "tile_negatives", "device")}
+                                                        "tile_negatives", "device", "hot_row_cap", "sampler")}
     if host:
         h = _cluster.connect_separate(host)
         h.load(path, engine_opts)
@@ -196,7 +200,7 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
                          max_grad=float(pcfg.get("max_grad", 0.0)),
                          neg_sharing=pcfg.get("neg_sharing", "pair"),
                          tile_centres=int(pcfg.get("tile_centres", 128)),
-                         tile_negatives=int(pcfg.get("tile_negatives", 64)))
+                         tile_negatives=int(pcfg.get("tile_negatives", 32)))
         opts = engine_options_from_params(self)
         handle = open_handle_for_fit(cfg, vocab.counts, self.getParameterServerHost(),
                                      self.getNumParameterServers(), opts)

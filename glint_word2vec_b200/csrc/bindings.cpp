@@ -26,79 +26,6 @@ void check_launch(const char* what) {
     TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e));
 }
 
-void sgns_step(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n_tokens, Tensor alias,
-               Tensor stats, int64_t pos0, int64_t seed, int64_t iteration, int64_t window, int64_t negatives,
-               int64_t window_mode, double alpha, double max_grad, bool compute_loss, int64_t grid,
-               int64_t world, int64_t rank, int64_t tile_centers, int64_t slot_floats,
-               std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs, int64_t xbuf_mc,
-               c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing,
-               int64_t debug, int64_t variant, c10::optional<Tensor> exp_table) {
-    CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
-    CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
-    CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
-    CHECK_DT(alias, torch::kInt32); CHECK_DT(stats, torch::kFloat32);
-    TORCH_CHECK(syn0.size(1) % 4 == 0, "row stride must be a multiple of 4 floats");
-    TORCH_CHECK(syn0.size(1) <= 1024, "at most 1024 columns per shard are supported");
-    c10::cuda::CUDAGuard guard(syn0.device());
-    gw2v::SgnsParams p{};
-    p.syn0 = syn0.data_ptr<float>();
-    p.syn1 = syn1.data_ptr<float>();
-    p.tokens = tokens.data_ptr<int>();
-    p.sent_id = sent_id.data_ptr<int>();
-    p.n_tokens = n_tokens.data_ptr<int>();
-    p.alias = reinterpret_cast<const int2*>(alias.data_ptr<int>());
-    p.stats = stats.data_ptr<float>();
-    p.pos0 = (unsigned long long)pos0;
-    p.seed_lo = (uint32_t)((uint64_t)seed & 0xFFFFFFFFull);
-    p.seed_hi = (uint32_t)(((uint64_t)seed >> 32) & 0xFFFFFFFFull);
-    p.iteration = (uint32_t)iteration;
-    p.vocab = (int)syn0.size(0);
-    p.K = (int)syn0.size(1);
-    p.window = (int)window; p.negatives = (int)negatives; p.window_mode = (int)window_mode;
-    p.alpha = (float)alpha; p.max_grad = (float)max_grad; p.compute_loss = compute_loss ? 1 : 0;
-    p.exp_table = nullptr;
-    if (exp_table.has_value()) {
-        CHECK_CUDA(*exp_table); CHECK_CONTIG(*exp_table); CHECK_DT(*exp_table, torch::kFloat32);
-        TORCH_CHECK(exp_table->numel() == 1000, "exp_table must have 1000 entries");
-        p.exp_table = exp_table->data_ptr<float>();
-    }
-    p.debug = (int)debug;
-    p.world = (int)world; p.rank = (int)rank;
-    p.tile_centers = (int)tile_centers; p.slot_floats = (int)slot_floats;
-    if (world > 1) {
-        TORCH_CHECK(world <= gw2v::MAX_WORLD, "world size > 8 not supported");
-        TORCH_CHECK((int64_t)xbuf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world, "peer pointer lists");
-        TORCH_CHECK(cta_seq.has_value() && error_flag.has_value(), "cta_seq/error_flag required");
-        TORCH_CHECK(variant >= 1 || (tile_centers >= 1 && tile_centers <= 256), "tile_centers must be in [1, 256]");
-        for (int r = 0; r < world; ++r) {
-            p.xbuf[r] = reinterpret_cast<float*>(xbuf_ptrs[r]);
-            p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
-        }
-        p.xbuf_mc = reinterpret_cast<float*>(xbuf_mc);
-        p.cta_seq = reinterpret_cast<uint32_t*>(cta_seq->data_ptr<int>());
-        p.error_flag = error_flag->data_ptr<int>();
-        p.timing = timing.has_value() ? reinterpret_cast<unsigned long long*>(timing->data_ptr<int64_t>()) : nullptr;
-        if (variant == 2) {
-            TORCH_CHECK(gw2v::sgns_group_multi_supported(p.K, p.window, p.negatives), "group-multi kernel: unsupported shape");
-            gw2v::launch_sgns_group_multi(p, (int)grid, p.cta_seq, cur_stream());
-        } else if (variant == 1) {
-            TORCH_CHECK(gw2v::sgns_pipe_multi_supported(p.K, p.window, p.negatives), "pipe-multi kernel: unsupported shape");
-            gw2v::launch_sgns_pipe_multi(p, (int)grid, p.cta_seq, cur_stream());
-        } else {
-            gw2v::launch_sgns_multi(p, (int)grid, cur_stream());
-        }
-    } else if (variant == 2) {
-        TORCH_CHECK(gw2v::sgns_group_supported(p.K, p.window, p.negatives), "group kernel does not support this shape");
-        gw2v::launch_sgns_group(p, (int)grid, cur_stream());
-    } else if (variant == 1) {
-        TORCH_CHECK(gw2v::sgns_pipe_supported(p.K, p.window, p.negatives), "pipe kernel does not support this shape");
-        gw2v::launch_sgns_pipe(p, (int)grid, cur_stream());
-    } else {
-        gw2v::launch_sgns_single(p, (int)grid, cur_stream());
-    }
-    check_launch("sgns_step");
-}
-
 // pair generation + the pair-parallel training kernel (single shard or column shards with in-kernel exchange)
 void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Tensor n_tokens, int64_t max_tokens,
                      Tensor alias, Tensor stats, int64_t pos0, int64_t seed, int64_t iteration, int64_t window,
@@ -107,7 +34,8 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
                      std::vector<int64_t> flag_ptrs, c10::optional<Tensor> warp_seq, c10::optional<Tensor> error_flag,
                      c10::optional<Tensor> timing, int64_t debug, Tensor cinfo, Tensor pair_off, Tensor n_pairs,
                      Tensor desc, Tensor tile_ws, int64_t xbuf_mc, int64_t share_centre,
-                     c10::optional<Tensor> exp_table) {
+                     c10::optional<Tensor> exp_table, c10::optional<Tensor> row_scale0,
+                     c10::optional<Tensor> row_scale1) {
     CHECK_CUDA(syn0); CHECK_CUDA(syn1); CHECK_CONTIG(syn0); CHECK_CONTIG(syn1);
     CHECK_DT(syn0, torch::kFloat32); CHECK_DT(syn1, torch::kFloat32);
     CHECK_DT(tokens, torch::kInt32); CHECK_DT(sent_id, torch::kInt32); CHECK_DT(n_tokens, torch::kInt32);
@@ -117,7 +45,7 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     TORCH_CHECK(gw2v::sgns_pairs_supported((int)syn0.size(1), (int)window, (int)negatives), "sgns_pairs: unsupported shape");
     const int pd = gw2v::pairgen_desc_ints((int)negatives);
     TORCH_CHECK(cinfo.numel() >= max_tokens && pair_off.numel() >= max_tokens, "pairgen workspaces too small");
-    TORCH_CHECK(desc.numel() >= max_tokens * 2 * window * pd, "descriptor buffer too small");
+    TORCH_CHECK(desc.numel() >= max_tokens * 2 * window * pd * gw2v::pairgen_splits((int)negatives), "descriptor buffer too small");
     TORCH_CHECK(tile_ws.numel() >= gw2v::pairgen_max_blocks((int)max_tokens), "tile workspace too small");
     TORCH_CHECK(max_tokens <= gw2v::pairgen_max_tokens(), "step too large for the pair generator (max ", gw2v::pairgen_max_tokens(), " tokens)");
     c10::cuda::CUDAGuard guard(syn0.device());
@@ -145,6 +73,14 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     }
     p.debug = (int)debug;
     p.world = (int)world; p.rank = (int)rank;
+    if (row_scale0.has_value() && row_scale1.has_value()) {        // hot-row damping tables (first hot_rows rows)
+        CHECK_CUDA(*row_scale0); CHECK_CUDA(*row_scale1); CHECK_DT(*row_scale0, torch::kFloat32);
+        CHECK_DT(*row_scale1, torch::kFloat32); CHECK_CONTIG(*row_scale0); CHECK_CONTIG(*row_scale1);
+        TORCH_CHECK(row_scale0->numel() == row_scale1->numel(), "row scale tables must have the same length");
+        p.hot_rows = (int)std::min<int64_t>(row_scale0->numel(), syn0.size(0));
+        p.row_scale0 = row_scale0->data_ptr<float>();
+        p.row_scale1 = row_scale1->data_ptr<float>();
+    }
     gw2v::launch_pairgen(p.tokens, p.sent_id, p.n_tokens, (int)max_tokens, p.alias, p.vocab, p.seed_lo, p.seed_hi,
                          p.iteration, p.pos0, p.window, p.window_mode, p.negatives, (int)share_centre,
                          reinterpret_cast<uint32_t*>(cinfo.data_ptr<int>()), pair_off.data_ptr<int>(),
@@ -167,12 +103,6 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
         gw2v::launch_sgns_pairs(p, desc.data_ptr<int>(), n_pairs.data_ptr<int>(), pd, (int)grid, cur_stream());
     }
     check_launch("sgns_step_pairs");
-}
-
-int64_t sgns_single_grid(int64_t K, int64_t device) { return gw2v::sgns_single_grid((int)K, (int)device); }
-int64_t sgns_multi_max_grid(int64_t K, int64_t window, int64_t negatives, int64_t tile_centers, int64_t device) {
-    c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
-    return gw2v::sgns_multi_max_grid((int)K, (int)window, (int)negatives, (int)tile_centers, (int)device);
 }
 
 void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thresh, int64_t seed,
@@ -515,7 +445,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("serve_topk_owned_push", &serve_topk_owned_push);
     m.def("serve_topk_final", &serve_topk_final);
     m.def("serve_push_block", &serve_push_block);
-    m.def("sgns_step", &sgns_step);
     m.def("sgns_step_pairs", &sgns_step_pairs);
     m.def("sgns_pairs_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_pairs_supported((int)K, (int)w, (int)n); });
     m.def("sgns_pairs_grid", [](int64_t K, int64_t dev, bool multi) {
@@ -525,32 +454,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         int w, ns, sf; gw2v::sgns_pairs_multi_geometry(&w, &ns, &sf); return std::vector<int64_t>{w, ns, sf}; });
     m.def("pairgen_max_blocks", [](int64_t t) { return (int64_t)gw2v::pairgen_max_blocks((int)t); });
     m.def("pairgen_desc_ints", [](int64_t n) { return (int64_t)gw2v::pairgen_desc_ints((int)n); });
-    m.def("sgns_single_grid", &sgns_single_grid);
-    m.def("sgns_multi_max_grid", &sgns_multi_max_grid);
-    m.def("sgns_pipe_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_pipe_supported((int)K, (int)w, (int)n); });
-    m.def("sgns_pipe_grid", [](int64_t K, int64_t n, int64_t dev) {
-        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
-        return (int64_t)gw2v::sgns_pipe_grid((int)K, (int)n, (int)dev); });
-    m.def("sgns_group_supported", [](int64_t K, int64_t w, int64_t n) { return gw2v::sgns_group_supported((int)K, (int)w, (int)n); });
-    m.def("sgns_group_grid", [](int64_t K, int64_t dev) {
-        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
-        return (int64_t)gw2v::sgns_group_grid((int)K, (int)dev); });
-    m.def("sgns_group_multi_supported", [](int64_t K, int64_t w, int64_t n) {
-        return gw2v::sgns_group_multi_supported((int)K, (int)w, (int)n); });
-    m.def("sgns_group_multi_geometry", [](int64_t K, int64_t dev) {
-        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
-        int grid, warps, nslot, sf;
-        gw2v::sgns_group_multi_geometry((int)K, (int)dev, &grid, &warps, &nslot, &sf);
-        return std::vector<int64_t>{grid, warps, nslot, sf}; });
-    m.def("sgns_pipe_multi_supported", [](int64_t K, int64_t w, int64_t n) {
-        return gw2v::sgns_pipe_multi_supported((int)K, (int)w, (int)n); });
-    m.def("sgns_pipe_multi_geometry", [](int64_t K, int64_t n, int64_t dev) {
-        c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
-        int grid, warps, nslot, sf;
-        gw2v::sgns_pipe_multi_geometry((int)K, (int)n, (int)dev, &grid, &warps, &nslot, &sf);
-        return std::vector<int64_t>{grid, warps, nslot, sf}; });
-    m.def("sgns_multi_smem_bytes", [](int64_t w, int64_t n, int64_t tb) {
-        return (int64_t)gw2v::sgns_multi_smem_bytes((int)w, (int)n, (int)tb); });
+    m.def("pairgen_splits", [](int64_t n) { return (int64_t)gw2v::pairgen_splits((int)n); });
     m.def("subsample_compact", &subsample_compact);
     m.def("subsample_max_blocks", &subsample_max_blocks);
     m.def("zipf_stream", &zipf_stream);

@@ -119,8 +119,13 @@ void sgns_step_tile(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Ten
     l.cinfo = reinterpret_cast<const uint32_t*>(cinfo.data_ptr<int>());
     l.tile_negs = tile_negs.data_ptr<int>();
     l.n_pairs = n_pairs.data_ptr<int>();
-    l.row_scale0 = opt_f(row_scale0, syn0.size(0), "row_scale0");
-    l.row_scale1 = opt_f(row_scale1, syn0.size(0), "row_scale1");
+    TORCH_CHECK(row_scale0.has_value() == row_scale1.has_value(), "row_scale0 / row_scale1 come together");
+    if (row_scale0.has_value()) {
+        TORCH_CHECK(row_scale0->numel() == row_scale1->numel(), "row scale tables must have the same length");
+        p.hot_rows = (int)std::min<int64_t>(row_scale0->numel(), syn0.size(0));
+        p.row_scale0 = opt_f(row_scale0, 0, "row_scale0");
+        p.row_scale1 = opt_f(row_scale1, 0, "row_scale1");
+    }
     l.dbg = opt_f(dbg, 128 * (160 + tile_negatives), "dbg");
     l.max_tokens = (int)max_tokens;
     l.tile_negatives = (int)tile_negatives;

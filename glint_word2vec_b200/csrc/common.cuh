@@ -90,6 +90,11 @@ __device__ __forceinline__ float sgns_coeff(float f, float label, float alpha, f
     return g;
 }
 
+// per-row update scale of the hot-row damping (1 beyond the first `hot_rows` rows)
+__device__ __forceinline__ float row_scale(const float* __restrict__ tab, int hot_rows, int row) {
+    return (tab != nullptr && row < hot_rows) ? __ldg(tab + row) : 1.0f;
+}
+
 // softplus on the clipped dot: -log sigma(f) = softplus(-f)
 __device__ __forceinline__ float softplus_clipped(float x) {
     x = fminf(fmaxf(x, -MAX_EXP), MAX_EXP);

@@ -21,6 +21,8 @@ void launch_init_syn0(float* syn0, long long vocab, int K, int col_start, int ve
 // pairgen.cu
 int pairgen_max_blocks(int max_tokens);
 int pairgen_desc_ints(int negatives);
+int pairgen_splits(int negatives);       // descriptors per pair: 1 up to 7 negatives, then one per 7
+int pairgen_max_negatives();
 int pairgen_max_tokens();
 void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, int max_tokens, const int2* alias,
                     int vocab, uint32_t seed_lo, uint32_t seed_hi, uint32_t iteration, unsigned long long pos0,

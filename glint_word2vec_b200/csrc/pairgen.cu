@@ -109,13 +109,19 @@ pair_tile_scan_kernel(int* __restrict__ tile_sum, int ntiles, int* __restrict__ 
     if (tid < ntiles) tile_sum[tid] = wt[warp] + x - v;          // exclusive prefix of tile tid
 }
 
-// one thread per (centre, offset slot q); PD ints per descriptor: {wtok, ctok, negs[n], pad}
+// one thread per (centre, offset slot q).  Descriptor = PD ints {wtok, ctok, negs[<= 7], pad}; a negative slot that
+// is not used holds -1.  More than 7 negatives per pair (the reference accepts any n > 0, MLLIB:184-190; BASELINE.json
+// config 4 uses n = 10) are spread over `splits` consecutive descriptors of the same pair: the first carries the context
+// and negatives 0..6, the following ones carry the next 7 negatives each and mark their context word as inactive (bit 31:
+// it is still needed for the "negative == positive is skipped" rule).  The training kernels therefore never see more than
+// 1 + 7 rows per descriptor whatever n is.
+constexpr int PG_MAXNEG = 21;
 __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __restrict__ n_tokens,
                                  const uint32_t* __restrict__ cinfo, const int* __restrict__ pair_off,
                                  const int* __restrict__ tile_prefix,
                                  const int2* __restrict__ alias, int vocab, uint32_t seed_lo, uint32_t seed_hi,
                                  uint32_t iteration, unsigned long long pos0, int window, int negatives, int slots,
-                                 int pd, int share_centre, int* __restrict__ desc) {
+                                 int pd, int splits, int share_centre, int* __restrict__ desc) {
     const int T = *n_tokens;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i = gid / slots;
@@ -127,7 +133,8 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     const int lo = -(int)(info >> 24);
     const int off = lo + q;
     const int rank = __popc(mask & ((1u << q) - 1u));
-    int* e = desc + (size_t)(__ldg(tile_prefix + (int)(i / PC_TILE)) + __ldg(pair_off + i) + rank) * pd;
+    const size_t pair = (size_t)(__ldg(tile_prefix + (int)(i / PC_TILE)) + __ldg(pair_off + i) + rank);
+    int* e = desc + pair * (size_t)splits * pd;
     const int ctok = __ldg(tokens + i + off);
     const int wtok = __ldg(tokens + i);
     const int ncalls = (negatives + 1) >> 1;
@@ -135,33 +142,55 @@ __global__ void pair_fill_kernel(const int* __restrict__ tokens, const int* __re
     const int slot = share_centre ? 0 : off + window;     // neg_sharing="centre": one draw per centre
     // all Philox calls first, then all alias-table reads in flight together (they are independent random
     // 8-byte reads into an 80 MB table), then the selects; the descriptor leaves as 16-byte stores
-    uint32_t idx[8], sel[8];
-    int2 ent[8];
+    if (splits == 1) {
+        uint32_t idx[8], sel[8];
+        int2 ent[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (c < ncalls) {
-            const uint4 r = rand4(seed_lo, seed_hi, sw, pos0 + (unsigned long long)i, (uint32_t)(slot * ncalls + c));
-            idx[2 * c] = __umulhi(r.x, (uint32_t)vocab); sel[2 * c] = r.y;
-            idx[2 * c + 1] = __umulhi(r.z, (uint32_t)vocab); sel[2 * c + 1] = r.w;
+        for (int c = 0; c < 4; ++c) {
+            if (c < ncalls) {
+                const uint4 r = rand4(seed_lo, seed_hi, sw, pos0 + (unsigned long long)i, (uint32_t)(slot * ncalls + c));
+                idx[2 * c] = __umulhi(r.x, (uint32_t)vocab); sel[2 * c] = r.y;
+                idx[2 * c + 1] = __umulhi(r.z, (uint32_t)vocab); sel[2 * c + 1] = r.w;
+            }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < negatives) ent[j] = __ldg(alias + idx[j]);
+        int w[12];
+        w[0] = wtok; w[1] = ctok;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            w[2 + j] = (j < negatives) ? ((sel[j] < (uint32_t)ent[j].x) ? (int)idx[j] : ent[j].y) : -1;
+        w[10] = w[11] = -1;
+        int4* e4 = reinterpret_cast<int4*>(e);                 // pd is a multiple of 4 ints: 16-byte aligned
+        e4[0] = make_int4(w[0], w[1], w[2], w[3]);
+        e4[1] = make_int4(w[4], w[5], w[6], w[7]);
+        if (pd > 8) e4[2] = make_int4(w[8], w[9], w[10], w[11]);
+        return;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (j < negatives) ent[j] = __ldg(alias + idx[j]);
-    int w[12];
-    w[0] = wtok; w[1] = ctok;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        w[2 + j] = (j < negatives) ? ((sel[j] < (uint32_t)ent[j].x) ? (int)idx[j] : ent[j].y) : 0;
-    w[10] = w[11] = 0;
-    int4* e4 = reinterpret_cast<int4*>(e);                 // pd is a multiple of 4 ints: 16-byte aligned
-    e4[0] = make_int4(w[0], w[1], w[2], w[3]);
-    e4[1] = make_int4(w[4], w[5], w[6], w[7]);
-    if (pd > 8) e4[2] = make_int4(w[8], w[9], w[10], w[11]);
+    int neg[PG_MAXNEG + 1];
+    for (int c = 0; c < ncalls; ++c) {
+        const uint4 r = rand4(seed_lo, seed_hi, sw, pos0 + (unsigned long long)i, (uint32_t)(slot * ncalls + c));
+        neg[2 * c] = alias_sample(alias, (uint32_t)vocab, r.x, r.y);
+        neg[2 * c + 1] = alias_sample(alias, (uint32_t)vocab, r.z, r.w);
+    }
+    for (int sp = 0; sp < splits; ++sp) {
+        int w[12];
+        w[0] = wtok;
+        w[1] = sp == 0 ? ctok : (int)((uint32_t)ctok | 0x80000000u);
+        for (int j = 0; j < 7; ++j) w[2 + j] = (7 * sp + j < negatives) ? neg[7 * sp + j] : -1;
+        w[9] = w[10] = w[11] = -1;
+        int4* e4 = reinterpret_cast<int4*>(e + (size_t)sp * pd);
+        e4[0] = make_int4(w[0], w[1], w[2], w[3]);
+        e4[1] = make_int4(w[4], w[5], w[6], w[7]);
+        e4[2] = make_int4(w[8], w[9], w[10], w[11]);
+    }
 }
 
 int pairgen_max_blocks(int max_tokens) { return (max_tokens + PC_TILE - 1) / PC_TILE + 1; }
-int pairgen_desc_ints(int negatives) { return ((2 + negatives) + 3) / 4 * 4; }
+int pairgen_splits(int negatives) { return negatives <= 7 ? 1 : (negatives + 6) / 7; }
+int pairgen_desc_ints(int negatives) { return negatives <= 7 ? ((2 + negatives) + 3) / 4 * 4 : 12; }
+int pairgen_max_negatives() { return PG_MAXNEG; }
 int pairgen_max_tokens() { return 1024 * PC_TILE; }
 
 // grid is sized from the host-side upper bound `max_tokens` (the device count may be smaller after
@@ -188,7 +217,8 @@ void launch_pairgen(const int* tokens, const int* sent_id, const int* n_tokens, 
     pair_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tokens, n_tokens, cinfo, pair_off, tile_sum,
                                                                          alias, vocab, seed_lo, seed_hi, iteration,
                                                                          pos0, window, negatives, slots,
-                                                                         pairgen_desc_ints(negatives), share_centre, desc);
+                                                                         pairgen_desc_ints(negatives), pairgen_splits(negatives),
+                                                                         share_centre, desc);
 }
 
 // window masks + total pair count only: what the tensor-core tile kernel needs (it derives the pairs from the masks)

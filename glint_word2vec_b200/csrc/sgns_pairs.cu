@@ -86,13 +86,14 @@ __device__ __forceinline__ void pk_load_desc(const int* __restrict__ desc, long 
     d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
     d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
     if (pd > 8) { const int4 c = __ldg(e + 2); d.w[8] = c.x; d.w[9] = c.y; d.w[10] = c.z; d.w[11] = c.w; }
-    else { d.w[8] = d.w[9] = d.w[10] = d.w[11] = 0; }
+    else { d.w[8] = d.w[9] = d.w[10] = d.w[11] = -1; }             // -1 = unused negative slot
 }
 
 // ------------------------------------------------------------------------------------------ single shard
 template <int G, int CHUNKS, int MINB>
 __global__ void __launch_bounds__(PK_THREADS, MINB)
-sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr, const int pd) {
+sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr, const int pd,
+                  const int splits) {
     constexpr int P = 32 / G;
     const int lane = threadIdx.x & 31;
     const int K = p.K;
@@ -102,7 +103,8 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
     int coff[CHUNKS];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) { coff[c] = (c * G + lg) * 4; act[c] = coff[c] < K; }
-    const long long n_pairs = *n_pairs_ptr;
+    const long long n_real_pairs = *n_pairs_ptr;
+    const long long n_pairs = n_real_pairs * splits;              // descriptors (n > 7: several per pair, pairgen.cu)
     const long long nsteps = (n_pairs + P - 1) / P;
     const long long warp_global = ((long long)blockIdx.x * PK_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * PK_THREADS) >> 5;
@@ -115,7 +117,9 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
         const bool gvalid = pair < n_pairs;
         PairDesc d;
         pk_load_desc(desc, gvalid ? pair : 0, pd, d);
-        const int ctok = d.w[1];
+        const int ctok = d.w[1] & 0x7fffffff;                     // bit 31: context row inactive (continuation descriptor)
+        const bool ctx_on = d.w[1] >= 0;
+        d.w[1] = ctok;
         float* urow = p.syn0 + (size_t)d.w[0] * K;
         float u[CHUNKS][4], du[CHUNKS][4];
         float v[8][CHUNKS][4];
@@ -128,7 +132,7 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            ract[r] = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
+            ract[r] = gvalid && (r == 0 ? ctx_on : (d.w[r + 1] >= 0 && d.w[r + 1] != ctok));   // unused slots hold -1
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
@@ -162,6 +166,7 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
             const float g = __shfl_sync(0xffffffffu, gmine, pk_lane_of_row<G>(r), G);
             if (!ract[r]) continue;
             float* vrow = p.syn1 + (size_t)d.w[r + 1] * K;
+            const float gs = g * row_scale(p.row_scale1, p.hot_rows, d.w[r + 1]);       // hot-row damping of this v row
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
                 if (!act[c]) continue;
@@ -169,19 +174,24 @@ sgns_pairs_kernel(const SgnsParams p, const int* __restrict__ desc, const int* _
 #pragma unroll
                 for (int el = 0; el < 4; ++el) {
                     du[c][el] = fmaf(g, v[r][c][el], du[c][el]);
-                    gu[el] = g * u[c][el];
+                    gu[el] = gs * u[c][el];
                 }
                 if (!(p.debug & 1)) pk_red4(vrow + coff[c], gu);
             }
         }
         if (gvalid && !(p.debug & 2)) {
+            const float su = row_scale(p.row_scale0, p.hot_rows, d.w[0]);
 #pragma unroll
-            for (int c = 0; c < CHUNKS; ++c)
-                if (act[c]) pk_red4(urow + coff[c], du[c]);
+            for (int c = 0; c < CHUNKS; ++c) {
+                if (!act[c]) continue;
+#pragma unroll
+                for (int el = 0; el < 4; ++el) du[c][el] *= su;
+                pk_red4(urow + coff[c], du[c]);
+            }
         }
     }
 
-    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_pairs; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_real_pairs; }
     if (p.compute_loss) {
         loss = warp_sum(loss);
         maxdot = warp_max(maxdot);
@@ -208,7 +218,7 @@ struct PkWarpSmem {
 template <int G, int CHUNKS, int MINB, int LAG>
 __global__ void __launch_bounds__(PK_THREADS, MINB)
 sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const int* __restrict__ n_pairs_ptr,
-                        const int pd, uint32_t* warp_seq) {
+                        const int pd, uint32_t* warp_seq, const int splits) {
     constexpr int P = 32 / G;
     constexpr int BS = PK_BATCH / P;           // steps per batch
     static_assert(LAG % PK_BATCH == 0 && LAG <= PK_LAG, "lag must be whole batches");
@@ -229,7 +239,8 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
     int coff[CHUNKS];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) { coff[c] = (c * G + lg) * 4; act[c] = coff[c] < K; }
-    const long long n_pairs = *n_pairs_ptr;
+    const long long n_real_pairs = *n_pairs_ptr;
+    const long long n_pairs = n_real_pairs * splits;              // descriptors (n > 7: several per pair, pairgen.cu)
     const long long nsteps = (n_pairs + P - 1) / P;
     const int gwarp = blockIdx.x * (PK_THREADS / 32) + warp;            // identical on every rank
     const int n_warps = gridDim.x * (PK_THREADS / 32);
@@ -259,7 +270,9 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             dB.w[0] = a.x; dB.w[1] = a.y; dB.w[2] = a.z; dB.w[3] = a.w;
             dB.w[4] = b2.x; dB.w[5] = b2.y; dB.w[6] = b2.z; dB.w[7] = b2.w;
             dB.w[8] = c2.x; dB.w[9] = c2.y; dB.w[10] = c2.z; dB.w[11] = c2.w;
-            const int ctokB = dB.w[1];
+            const int ctokB = dB.w[1] & 0x7fffffff;
+            const bool ctxB = dB.w[1] >= 0;
+            dB.w[1] = ctokB;
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
@@ -268,7 +281,7 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                ractB[r] = gvalidB && r <= n && (r == 0 || dB.w[r + 1] != ctokB);
+                ractB[r] = gvalidB && (r == 0 ? ctxB : (dB.w[r + 1] >= 0 && dB.w[r + 1] != ctokB));
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
@@ -283,7 +296,8 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             const bool gvalid = pair < n_pairs;
             PairDesc d;
             pk_load_desc(desc, gvalid ? pair : 0, pd, d);
-            const int ctok = d.w[1];
+            const int ctok = d.w[1] & 0x7fffffff;                 // the stash keeps the raw word (flag included) for pass B
+            const bool ctx_on = d.w[1] >= 0;
             if (lg == 0) {
                 int4* st = reinterpret_cast<int4*>(dstash + ((k % RFS) * P + grp) * 12);
                 st[0] = make_int4(d.w[0], d.w[1], d.w[2], d.w[3]);
@@ -300,12 +314,12 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const bool ra = gvalid && r <= n && (r == 0 || d.w[r + 1] != ctok);
+                const bool ra = gvalid && (r == 0 ? ctx_on : (d.w[r + 1] >= 0 && d.w[r + 1] != ctok));
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
                     for (int el = 0; el < 4; ++el) v[r][c][el] = 0.f;
-                    if (ra && act[c]) pk_ld4(p.syn1 + (size_t)d.w[r + 1] * K + coff[c], v[r][c]);
+                    if (ra && act[c]) pk_ld4(p.syn1 + (size_t)(r == 0 ? ctok : d.w[r + 1]) * K + coff[c], v[r][c]);
                 }
             }
             float f[8];
@@ -432,6 +446,7 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 const float g = __shfl_sync(0xffffffffu, gmine, pk_lane_of_row<G>(r), G);
                 if (!ract[r]) continue;
                 float* vrow = p.syn1 + (size_t)d.w[r + 1] * K;
+                const float gs = g * row_scale(p.row_scale1, p.hot_rows, d.w[r + 1]);   // hot-row damping of this v row
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
                     if (!act[c]) continue;
@@ -439,21 +454,26 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
 #pragma unroll
                     for (int el = 0; el < 4; ++el) {
                         du[c][el] = fmaf(g, v[r][c][el], du[c][el]);
-                        gu[el] = g * u[c][el];
+                        gu[el] = gs * u[c][el];
                     }
                     if (!(p.debug & 1)) pk_red4(vrow + coff[c], gu);
                 }
             }
             if (gvalid && !(p.debug & 2)) {
+                const float su = row_scale(p.row_scale0, p.hot_rows, d.w[0]);
 #pragma unroll
-                for (int c = 0; c < CHUNKS; ++c)
-                    if (act[c]) pk_red4(urow + coff[c], du[c]);
+                for (int c = 0; c < CHUNKS; ++c) {
+                    if (!act[c]) continue;
+#pragma unroll
+                    for (int el = 0; el < 4; ++el) du[c][el] *= su;
+                    pk_red4(urow + coff[c], du[c]);
+                }
             }
         }
     }
     if (lane == 0) warp_seq[gwarp] = seq0 + (uint32_t)((nk + BS - 1) / BS);
 
-    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_pairs; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.stats[3] = (float)(*p.n_tokens); p.stats[0] = (float)n_real_pairs; }
     if (p.compute_loss) {
         loss = warp_sum(loss);
         maxdot = warp_max(maxdot);
@@ -477,7 +497,8 @@ static void pk_group(int K, int* G, int* chunks) {
 }
 
 bool sgns_pairs_supported(int K, int window, int negatives) {
-    return negatives >= 1 && negatives <= 7 && window >= 1 && window <= 11 && K % 4 == 0 && K <= 1024;
+    // more than 7 negatives per pair travel as several descriptors (pairgen.cu): up to 21
+    return negatives >= 1 && negatives <= 21 && window >= 1 && window <= 11 && K % 4 == 0 && K <= 1024;
 }
 
 static int pk_occ() {
@@ -538,15 +559,17 @@ void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats)
 }
 
 void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid, cudaStream_t stream) {
-#define CALL(GG, C, MB) sgns_pairs_kernel<GG, C, MB><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd)
+    const int splits = p.negatives <= 7 ? 1 : (p.negatives + 6) / 7;
+#define CALL(GG, C, MB) sgns_pairs_kernel<GG, C, MB><<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, splits)
     GW2V_PK_DISPATCH(p.K, CALL);
 #undef CALL
 }
 
 void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
                              uint32_t* warp_seq, cudaStream_t stream) {
+    const int splits = p.negatives <= 7 ? 1 : (p.negatives + 6) / 7;
 #define CALL(GG, C, MB) pk_multi_select<GG, C, MB>([&](auto kern) {                      \
-        kern<<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq); })
+        kern<<<grid, PK_THREADS, 0, stream>>>(p, desc, n_pairs, pd, warp_seq, splits); })
     GW2V_PK_DISPATCH(p.K, CALL);
 #undef CALL
 }

@@ -23,6 +23,13 @@ struct SgnsParams {
     int window, negatives, window_mode;   // window_mode 0 = reference (Q2), 1 = word2vec.c
     float alpha, max_grad;
     const float* exp_table;      // 1000-entry sigma table on [-6,6] (MLLIB:281-302 parity mode) or null = exact
+    // Hot-row damping: the update of row r of syn0 / syn1 is multiplied by row_scale{0,1}[r] for r < hot_rows (rows
+    // beyond are 1).  A device step applies thousands of stale, summed updates to the rows of very frequent words --
+    // the exploding-gradient hazard README.md:17-19 warns about, 10^3 times stronger here -- so their effective
+    // learning rate is capped (models/engine.py::row_scales).  null / 0 = off.
+    const float* row_scale0;
+    const float* row_scale1;
+    int hot_rows;
     int compute_loss;
     int debug;                   // bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads (profiling);
                                  // bit3 single-GPU loopback of the exchange (profiling); bit4 random push delays (stress test)
@@ -38,18 +45,6 @@ struct SgnsParams {
     unsigned long long* timing;  // optional [grid*2]: accumulated wait ns, tiles (exposed all-reduce time)
 };
 
-// grid/block/smem helpers live in sgns_kernels.cu
-void launch_sgns_single(const SgnsParams& p, int grid, cudaStream_t stream);
-void launch_sgns_multi(const SgnsParams& p, int grid, cudaStream_t stream);
-int sgns_multi_max_grid(int K, int window, int negatives, int tile_centers, int device);
-int sgns_single_grid(int K, int device);
-size_t sgns_multi_smem_bytes(int window, int negatives, int tile_centers);
-
-// sgns_pipe.cu: per-warp TMA pipeline variant of the single-shard step
-bool sgns_pipe_supported(int K, int window, int negatives);
-int sgns_pipe_grid(int K, int negatives, int device);
-void launch_sgns_pipe(const SgnsParams& p, int grid, cudaStream_t stream);
-
 // sgns_pairs.cu: production step over pre-generated pair descriptors (pairgen.cu)
 bool sgns_pairs_supported(int K, int window, int negatives);
 int sgns_pairs_grid(int K, int device, bool multi);
@@ -57,20 +52,5 @@ void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats)
 void launch_sgns_pairs(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid, cudaStream_t stream);
 void launch_sgns_pairs_multi(const SgnsParams& p, const int* desc, const int* n_pairs, int pd, int grid,
                              uint32_t* warp_seq, cudaStream_t stream);
-
-// sgns_group.cu: register-path kernel with lane groups (short rows / high occupancy)
-bool sgns_group_supported(int K, int window, int negatives);
-int sgns_group_grid(int K, int device);
-void launch_sgns_group(const SgnsParams& p, int grid, cudaStream_t stream);
-
-// sgns_group_multi.cu: lane-group register path with the in-kernel NVLink all-reduce (world > 1)
-bool sgns_group_multi_supported(int K, int window, int negatives);
-void sgns_group_multi_geometry(int K, int device, int* grid, int* warps, int* nslot, int* slot_floats);
-void launch_sgns_group_multi(const SgnsParams& p, int grid, uint32_t* warp_seq, cudaStream_t stream);
-
-// sgns_pipe_multi.cu: the pipeline with the in-kernel NVLink all-reduce (world > 1)
-bool sgns_pipe_multi_supported(int K, int window, int negatives);
-void sgns_pipe_multi_geometry(int K, int negatives, int device, int* grid, int* warps, int* nslot, int* slot_floats);
-void launch_sgns_pipe_multi(const SgnsParams& p, int grid, uint32_t* warp_seq, cudaStream_t stream);
 
 }  // namespace gw2v

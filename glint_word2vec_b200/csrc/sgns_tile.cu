@@ -85,8 +85,6 @@ struct TileArgs {
     const uint32_t* cinfo;        // [T] window masks from pair_count_kernel
     const int* tile_negs;         // [ntiles_max, NN]
     const int* n_pairs;           // device scalar (pair_tile_scan_kernel)
-    const float* row_scale0;      // optional per-row update scale of syn0 / syn1 (hot-row damping), or null
-    const float* row_scale1;
     float* dbg;                   // optional debug dump of tile 0: S [128 x R] (band window + negatives)
 };
 
@@ -526,9 +524,9 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             // ---- rows this thread updates in the chunks of its group
             const int utok = (int)ldsu(sm, meta + row * 4);
             const bool u_on = m > 0;
-            const float su = (a.row_scale0 != nullptr && u_on) ? __ldg(a.row_scale0 + utok) : 1.f;
+            const float su = row_scale(p.row_scale0, p.hot_rows, utok);          // hot-row damping (sgns_params.h)
             const int ntok = row < NN ? (int)ldsu(sm, meta + (TL_T + TL_CTX + row) * 4) : 0;
-            const float sn = (a.row_scale1 != nullptr && row < NN) ? __ldg(a.row_scale1 + ntok) : 1.f;
+            const float sn = row_scale(p.row_scale1, p.hot_rows, ntok);
             // context rows owned by this thread: `row` and, in warp 3 of the group, also row 128 + lane
             uint32_t cm[2]; int ctok[2]; float cs[2];
 #pragma unroll
@@ -538,7 +536,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 if (rr < TL_CTX) {
                     cm[x] = ldsu(sm, C::MASK_OFF + rr * 4);
                     ctok[x] = (int)ldsu(sm, meta + (TL_T + rr) * 4);
-                    if (a.row_scale1 != nullptr && cm[x]) cs[x] = __ldg(a.row_scale1 + ctok[x]);
+                    cs[x] = row_scale(p.row_scale1, p.hot_rows, ctok[x]);
                 }
             }
             // ---- pass B: accumulators + positive terms -> 16-byte atomics
@@ -726,7 +724,7 @@ static int launch_tile_r(const SgnsParams& p, const TileLaunch& l, cudaStream_t 
     TileArgs a{};
     a.p = p;
     a.cinfo = l.cinfo; a.tile_negs = l.tile_negs; a.n_pairs = l.n_pairs;
-    a.row_scale0 = l.row_scale0; a.row_scale1 = l.row_scale1; a.dbg = l.dbg;
+    a.dbg = l.dbg;
     auto kern = sgns_tile_kernel<R, SLP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     kern<<<l.grid, TL_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tm0s, tm1s, a);

@@ -10,8 +10,6 @@ struct TileLaunch {
     const uint32_t* cinfo;        // [max_tokens] window masks (pair_count_kernel)
     int* tile_negs;               // [sgns_tile_max_tiles(max_tokens), tile_negatives] workspace
     const int* n_pairs;           // device scalar written by the pair-count scan
-    const float* row_scale0;      // optional [V] update scale per syn0 row (null = 1)
-    const float* row_scale1;      // optional [V] update scale per syn1 row
     float* dbg;                   // optional [128 * R] dump of tile 0's dot products (tests)
     int max_tokens;               // host-side upper bound of the step's token count
     int tile_negatives;           // 32 or 64

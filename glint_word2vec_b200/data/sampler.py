@@ -106,6 +106,31 @@ def unigram_alias(counts: np.ndarray, power: float = 0.75, use_native: bool = Tr
     return build_alias(np.asarray(counts, dtype=np.float64) ** power, use_native=use_native)
 
 
+def unigram_table_counts(counts: np.ndarray, table_size: int, power: float = 0.75) -> np.ndarray:
+    """How many of the ``table_size`` slots of word2vec.c's ``InitUnigramTable`` each word occupies (int64 [V]).
+
+    The reference's servers draw negatives as ``table[rand % unigramTableSize]`` from a table filled like
+    ``InitUnigramTable`` (MLLIB:239-244, ML:204-209, [G]): slot a belongs to word i, and i advances by at most one per
+    slot once ``a / size`` exceeds the cumulative ``cn^0.75`` mass.  The slot counts are that quantised distribution
+    exactly; ``sampler="table"`` feeds them to the alias sampler, which then draws from the same distribution as the
+    400 MB table without building it."""
+    cn = np.asarray(counts, dtype=np.float64) ** power
+    v = cn.shape[0]
+    cum = np.cumsum(cn / cn.sum())
+    idx = np.arange(v, dtype=np.int64)
+    first_after = np.floor(cum * table_size).astype(np.int64) + 1        # first slot a with a / size > cum[i]
+    last = np.maximum.accumulate(first_after - idx) + idx                 # i advances at most once per slot
+    last = np.minimum(last, table_size - 1)
+    last[-1] = table_size - 1                                             # `if (i >= vocab_size) i = vocab_size - 1`
+    prev = np.concatenate([[-1], last[:-1]])
+    return np.maximum(last - prev, 0)
+
+
+def unigram_table_alias(counts: np.ndarray, table_size: int, power: float = 0.75, use_native: bool = True) -> AliasTable:
+    """Alias table over the slot counts of the reference's unigram table (``sampler="table"`` parity mode)."""
+    return build_alias(unigram_table_counts(counts, table_size, power).astype(np.float64), use_native=use_native)
+
+
 def keep_thresholds(counts: np.ndarray, subsample_ratio: float, mode: str = "word2vec") -> np.ndarray:
     """uint32 threshold per word: a token is kept iff ``r <= thresh``.
 

@@ -29,7 +29,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 import torch
 
-from ..data.sampler import AliasTable, keep_thresholds, unigram_alias
+from ..data.sampler import AliasTable, keep_thresholds, unigram_alias, unigram_table_alias
 from ..parallel.comm import Comm
 from ..parallel.sharding import ColumnShard, make_shard
 from . import sgns
@@ -43,14 +43,34 @@ class EngineOptions:
     step_tokens: int = 0            # tokens per device step (0 = auto)
     subsample_ratio: float = 1e-6
     subsample_mode: str = "reference"   # "reference" (Q1: the reference's sub-sampling is inert) | "word2vec"
-    max_hot_updates: int = 256          # auto step size: expected stale summed updates on the hottest row per step
+    max_hot_updates: int = 256          # (damping off) auto step size: expected stale summed updates on the hottest row
+    # Hot-row damping: a device step applies the summed, stale updates of thousands of centres at once; the rows of very
+    # frequent words then receive hundreds of them and blow up (README.md:17-19 warns about exactly this; a 50-centre
+    # mini-batch of the reference is 10^3 times smaller).  The update of row r is scaled by min(1, hot_row_cap / c_r),
+    # c_r = expected number of concurrent updates of the row inside one staleness window -- an adaptive per-row
+    # learning rate that leaves all but the most frequent rows untouched.  Applied by the fused GPU kernels (pairs and
+    # tile); the un-fused path keeps the reference's exact semantics.  0 = off.
+    hot_row_cap: float = 32.0
+    # asynchronous data-parallel workers of the reference (``numPartitions``, MLLIB:122-126,345,392): P workers each
+    # have one mini-batch in flight against the same servers, i.e. the updates of P * batchSize centres are computed
+    # from the same stale rows.  The un-fused engine path reproduces that staleness: mini-batches of
+    # ``batch_size * num_partitions`` centres ("Use a small number for accuracy", MLLIB:120).  The GPU kernels always
+    # have thousands of centres in flight; there the value only enters the damping estimate.
+    num_partitions: int = 1
+    # negative sampler: "alias" = exact cn^0.75 through a Vose alias table (8 bytes per word); "table" = the quantised
+    # distribution of the reference's ``unigramTableSize``-slot table (MLLIB:239-244, ML:204-209), sampled through the
+    # same alias machinery (data/sampler.py::unigram_table_counts) -- a parity mode, no 400 MB table is built
+    sampler: str = "alias"
+    unigram_table_size: int = 100_000_000
     # How partial dots travel between column shards on GPUs:
     #   "auto"/"p2p": in-kernel st.global pushes into the peers' symmetric memory (the product)
     #   "nvls":       same kernel, one multimem.st per chunk on the NVLS multicast mapping
     #   "nccl"/"gloo": the un-fused Glint-style path (dotprod -> library all-reduce -> adjust) with the reference's
     #                  mini-batch semantics on any device; slow, kept for A/B runs and as the CPU path
     transport: str = "auto"
-    kernel: str = "auto"            # training kernel: auto | pairs | group | pipe | v1 (csrc/; env GW2V_*_KERNEL wins)
+    # training kernel: the pair kernel (csrc/sgns_pairs.cu) for neg_sharing pair/centre, the tcgen05 tile kernel
+    # (csrc/sgns_tile.cu) for neg_sharing="tile"; "auto" = that rule.  The round-1 generations live in csrc/legacy.
+    kernel: str = "auto"
     store_syn1: bool = True         # keep syn1neg in saves (retrainable)
 
     @classmethod
@@ -62,8 +82,10 @@ class EngineOptions:
     def __post_init__(self):
         if self.transport not in ("auto", "p2p", "nvls", "nccl", "gloo"):
             raise ValueError(f"unknown transport {self.transport!r}")
-        if self.kernel not in ("auto", "pairs", "group", "pipe", "v1"):
-            raise ValueError(f"unknown kernel {self.kernel!r}")
+        if self.kernel not in ("auto", "pairs", "tile"):
+            raise ValueError(f"unknown kernel {self.kernel!r} (the group/pipe/v1 kernels of round 1 are retired)")
+        if self.sampler not in ("alias", "table"):
+            raise ValueError(f"unknown sampler {self.sampler!r}")
 
 
 def _host_i32(x) -> np.ndarray:
@@ -139,10 +161,51 @@ class ShardEngine:
         if counts.shape[0] != self.cfg.vocab_size:
             raise ValueError("counts length != vocab size")
         self.noise_counts = counts
-        self.alias = unigram_alias(counts, 0.75, use_native=use_native)
+        if self.opts.sampler == "table":
+            self.alias = unigram_table_alias(counts, int(self.opts.unigram_table_size), 0.75, use_native=use_native)
+        else:
+            self.alias = unigram_alias(counts, 0.75, use_native=use_native)
         self.keep_thresh = keep_thresholds(counts, self.opts.subsample_ratio, self.opts.subsample_mode)
         if self.is_cuda:
             self._cuda.upload_noise(self.alias, self.keep_thresh)
+
+    def inflight_tokens(self, step_tokens: int) -> int:
+        """Staleness window: how many centres have their updates computed from the same (stale) rows."""
+        if not self.is_cuda or self.unfused:
+            return max(1, self.opts.batch_size) * max(1, self.opts.num_partitions)
+        if self.cfg.neg_sharing == "tile":
+            return min(int(step_tokens), 148 * self.cfg.tile_centres)      # one tile per SM in flight
+        return min(int(step_tokens), 4096)                                  # resident warps x pairs of the pair kernel
+
+    def row_scales(self, window_tokens: int):
+        """Hot-row damping tables ``(scale0, scale1)`` (float32, length = number of hot rows H; rows >= H are 1).
+
+        Expected concurrent updates of row r inside a window of W tokens (after sub-sampling):
+        ``c0 = W f_r m`` for the centre row, ``c1 = W m (f_r + n q_r)`` for the output row (context + negative
+        draws), with f the effective token frequency, q the noise distribution (cn^0.75) and m the mean number of
+        pairs per centre of the window mode; scale = min(1, hot_row_cap / c)."""
+        cap = float(self.opts.hot_row_cap)
+        if cap <= 0 or self.noise_counts is None:
+            return None
+        cnt = self.noise_counts.astype(np.float64)
+        keep = (self.keep_thresh.astype(np.float64) + 1.0) / 2.0 ** 32
+        eff = cnt * np.minimum(keep, 1.0)
+        f = eff / max(eff.sum(), 1.0)
+        q = cnt ** 0.75
+        q /= max(q.sum(), 1e-300)
+        w = self.cfg.window
+        if self.cfg.window_mode == "reference":
+            m = float(np.mean([max(0, 2 * b - 1) for b in range(w)]))
+        else:
+            m = float(w + 1)
+        W = float(max(1, window_tokens))
+        c0 = W * f * m
+        c1 = W * m * (f + self.cfg.negatives * q)
+        s0 = np.minimum(1.0, cap / np.maximum(c0, 1e-30)).astype(np.float32)
+        s1 = np.minimum(1.0, cap / np.maximum(c1, 1e-30)).astype(np.float32)
+        hot = np.nonzero((s0 < 1.0) | (s1 < 1.0))[0]
+        h = int(hot.max()) + 1 if hot.size else 0
+        return s0[:h], s1[:h]
 
     def set_weights(self, syn0_full: Optional[torch.Tensor], syn1_full: Optional[torch.Tensor] = None):
         """Install this rank's column slice of full [V, d] matrices."""
@@ -203,7 +266,9 @@ class ShardEngine:
         pairs = 0
         loss = 0.0
         maxdot = 0.0
-        bs = max(1, self.opts.batch_size)
+        # async workers = staleness window.  This path IS the reference's semantics (no damping: like the reference it
+        # relies on small mini-batches, "Use a small number [of partitions] for accuracy", MLLIB:120)
+        bs = max(1, self.opts.batch_size) * max(1, self.opts.num_partitions)
         for lo in range(0, t, bs):
             st = self._minibatch_cpu(tokens, sent_id, raw_pos0, iteration, alpha, lo, min(t, lo + bs))
             pairs += st.pairs

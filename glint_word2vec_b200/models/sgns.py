@@ -48,7 +48,7 @@ class SGNSConfig:
     # (docs/round2_tile_gemm.md); implemented by the oracle and the un-fused library path, not yet by a kernel.
     neg_sharing: str = "pair"
     tile_centres: int = 128
-    tile_negatives: int = 64
+    tile_negatives: int = 32
 
     def __post_init__(self):
         if self.neg_sharing not in ("pair", "centre", "tile"):

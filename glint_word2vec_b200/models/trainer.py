@@ -47,18 +47,22 @@ class TrainReport:
 def auto_step_tokens(engine: ShardEngine, corpus_tokens: int) -> int:
     """Tokens per device step.
 
-    On a GPU every centre of a step is in flight at once (thousands of warps), so
-    a row that occurs c times in the step receives c summed updates computed from
-    nearly the same stale values -- the asynchronous-SGD hazard the reference warns
-    about (README.md:17-19: "sensitive to very frequent words ... exploding
-    gradients").  The step is therefore sized so that the hottest word (after
-    sub-sampling) is expected at most ``max_hot_updates`` times per step, clamped to
-    [256, 256k] tokens; ``step_tokens`` overrides it."""
+    On a GPU every centre of a step is in flight at once (thousands of warps / 148 tiles), so a row that occurs c
+    times in the step receives c summed updates computed from nearly the same stale values -- the asynchronous-SGD
+    hazard the reference warns about (README.md:17-19: "sensitive to very frequent words ... exploding gradients").
+
+    * hot-row damping on (default, ``hot_row_cap > 0``): the hot rows are protected whatever the step size, so the step
+      is sized for statistical efficiency -- at least ~512 sequential steps per pass over a small corpus -- and capped
+      at 131 072 tokens (the benchmark step) for large ones;
+    * damping off: the hottest word (after sub-sampling) is expected at most ``max_hot_updates`` times per step.
+    Clamped to [256, 256k]; ``step_tokens`` overrides both."""
     opts = engine.opts
     if opts.step_tokens > 0:
         return opts.step_tokens
     if not engine.is_cuda:
         return max(opts.batch_size, min(1 << 16, corpus_tokens))
+    if opts.hot_row_cap > 0:
+        return int(max(256, min(1 << 17, corpus_tokens // 512)))
     f_max = 1.0
     if engine.alias is not None and engine.keep_thresh is not None and engine.noise_counts is not None:
         eff = engine.noise_counts.astype(np.float64) * (engine.keep_thresh.astype(np.float64) + 1.0) / 2.0 ** 32

@@ -95,8 +95,15 @@ class CudaShardOps:
                                                           engine.cfg.tile_centres, engine.cfg.tile_negatives):
             raise ValueError('neg_sharing="tile" on a GPU needs tile_centres=128, tile_negatives in {32, 64}, '
                              "window <= 11 and a multiple of 4 columns per shard")
-        self.row_scale0: Optional[torch.Tensor] = None     # optional per-row update scales (hot-row damping)
+        if not self._tile_mode and not _C.sgns_pairs_supported(self.K, engine.cfg.window, engine.cfg.negatives):
+            # no silent fall-back to a slower kernel: the limits are compile-time constants of csrc/pairgen.cu /
+            # csrc/sgns_pairs.cu.  transport="nccl" (un-fused torch path) runs any shape.
+            raise ValueError(f"the fused GPU step supports window <= 11, negatives <= 21 and at most 1024 columns per "
+                             f"shard (got window={engine.cfg.window}, negatives={engine.cfg.negatives}, "
+                             f"columns/shard={self.K}); use more shards or parameterServerConfig transport='nccl'")
+        self.row_scale0: Optional[torch.Tensor] = None     # per-row update scales of the first H rows (hot-row damping)
         self.row_scale1: Optional[torch.Tensor] = None
+        self._scale_window = -1
         self.tile_dbg: Optional[torch.Tensor] = None       # tests: dot products of tile 0
         # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self.exp_table = None
@@ -126,6 +133,7 @@ class CudaShardOps:
         return syn0, syn1
 
     def upload_noise(self, alias, keep_thresh: np.ndarray):
+        self._scale_window = -1               # the damping tables depend on the counts
         self.alias_dev = torch.from_numpy(alias.packed()).to(self.dev)
         self.keep_dev = torch.from_numpy(keep_thresh.view(np.int32).copy()).to(self.dev)
         self.subsample_active = bool((keep_thresh != U32_MAX).any())
@@ -170,7 +178,9 @@ class CudaShardOps:
             self.pg_desc = None
             self.tile_negs = torch.zeros(int(_C.sgns_tile_max_tiles(cap)) * cfg.tile_negatives, dtype=torch.int32, device=d)
         else:
-            self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd, dtype=torch.int32, device=d)
+            # n > 7 negatives: several descriptors per pair (csrc/pairgen.cu)
+            self.pg_desc = torch.empty(cap * 2 * cfg.window * self.pd * int(_C.pairgen_splits(cfg.negatives)),
+                                       dtype=torch.int32, device=d)
         self._cap = cap
 
     # ------------------------------------------------------------------ cross-shard exchange
@@ -179,44 +189,14 @@ class CudaShardOps:
         from ..parallel.symm import alloc_symmetric
         cfg = self.cfg
         dev_index = self.dev.index or 0
-        want = os.environ.get("GW2V_MULTI_KERNEL", self.e.opts.kernel)
-        pipe_ok = bool(_C.sgns_pipe_multi_supported(self.K, cfg.window, cfg.negatives))
-        group_ok = bool(_C.sgns_group_multi_supported(self.K, cfg.window, cfg.negatives))
-        pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))
-        if want == "auto":
-            want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
-        variant = 3 if (want == "pairs" and pairs_ok) else (
-            2 if (want == "group" and group_ok) else (1 if (want == "pipe" and pipe_ok) else 0))
-        if variant != 3 and self._share_centre:
-            raise RuntimeError('neg_sharing="centre" is implemented by the pairs kernel only')
-        if variant == 3:
-            grid = int(_C.sgns_pairs_grid(self.K, dev_index, True))
-            warps, nslot, slot_floats = [int(x) for x in _C.sgns_pairs_multi_geometry()]
-            tb = 0
-            units = grid * warps
-            xbytes = units * nslot * self.world * slot_floats * 4
-            nseq = units
-        elif variant >= 1:
-            geo = _C.sgns_group_multi_geometry(self.K, dev_index) if variant == 2 else \
-                _C.sgns_pipe_multi_geometry(self.K, cfg.negatives, dev_index)
-            grid, warps, nslot, slot_floats = [int(x) for x in geo]
-            tb = 0
-            units = grid * warps                      # one exchange ring per warp
-            xbytes = units * nslot * self.world * slot_floats * 4
-            nseq = units
-        else:
-            tb = int(os.environ.get("GW2V_TILE_CENTERS", "16"))
-            grid = int(_C.sgns_multi_max_grid(self.K, cfg.window, cfg.negatives, tb, dev_index))
-            maxpairs = tb * 2 * cfg.window
-            slot_floats = (maxpairs * (1 + cfg.negatives) + 3) // 4 * 4
-            units = grid                              # one exchange ring (2 slots) per CTA
-            xbytes = units * 2 * self.world * slot_floats * 4
-            nseq = grid
+        grid = int(_C.sgns_pairs_grid(self.K, dev_index, True))
+        warps, nslot, slot_floats = [int(x) for x in _C.sgns_pairs_multi_geometry()]
+        units = grid * warps                          # one exchange ring per warp
+        xbytes = units * nslot * self.world * slot_floats * 4
+        nseq = units
         fbytes = (units * self.world * 4 + 255) // 256 * 256
         xbytes = (xbytes + 255) // 256 * 256
         if self._loopback > 1:
-            if variant != 3:
-                raise RuntimeError("GW2V_LOOPBACK_WORLD supports the pairs kernel only")
             from ..parallel.symm import SymmBuffer
             local = torch.zeros(xbytes + fbytes, dtype=torch.uint8, device=self.dev)
             buf = SymmBuffer(local, [local.data_ptr()] * self.world, 0, None)
@@ -228,9 +208,8 @@ class CudaShardOps:
                 raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
             buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
         self._xchg = {
-            "buf": buf, "grid": grid, "tb": tb, "slot_floats": slot_floats, "variant": variant,
+            "buf": buf, "grid": grid, "slot_floats": slot_floats, "variant": "pairs",
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
-            "mc": buf.multicast_ptr,
             # NVLS multicast push (multimem.st) is opt-in: GW2V_NVLS=1 and a multicast mapping granted by the driver
             "mc_x": buf.multicast_ptr if (buf.multicast_ptr and self._want_nvls()) else 0,
             "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
@@ -342,10 +321,24 @@ class CudaShardOps:
             self._step_i += 1
         return stats
 
+    def _update_row_scales(self, t: int):
+        """Hot-row damping tables for a step of ``t`` tokens (models/engine.py::row_scales), cached per window size."""
+        w = self.e.inflight_tokens(t)
+        if w == self._scale_window:
+            return
+        self._scale_window = w
+        sc = self.e.row_scales(w)
+        if sc is None or sc[0].shape[0] == 0:
+            self.row_scale0 = self.row_scale1 = None
+        else:
+            self.row_scale0 = torch.from_numpy(sc[0]).to(self.dev)
+            self.row_scale1 = torch.from_numpy(sc[1]).to(self.dev)
+
     def _train_step_device_impl(self, tok_dev, sid_dev, t, raw_pos0, iteration, alpha) -> torch.Tensor:
         cfg = self.cfg
         e = self.e
         self._ensure_capacity(t)
+        self._update_row_scales(t)
         if self.world > 1 and self._xchg is None and not self._tile_mode:
             self._setup_exchange()
         if self.subsample_active:
@@ -361,10 +354,6 @@ class CudaShardOps:
             tok, sid = tok_dev, sid_dev
         self._stats_i = (self._stats_i + 1) % self._stats_ring.shape[0]
         stats = self._stats_ring[self._stats_i]
-        pairs_path = (not self._tile_mode) and ((self.world > 1 and self._xchg["variant"] == 3) or
-                                                (self.world == 1 and getattr(self, "_variant", None) == 3))
-        if not pairs_path and not self._tile_mode:
-            stats.zero_()                 # the pairs path zeroes them inside pair_tile_scan_kernel (one launch less)
         wm = WINDOW_MODES[cfg.window_mode]
         if self._tile_mode:
             if not hasattr(self, "_tile_grid"):
@@ -381,38 +370,25 @@ class CudaShardOps:
                               x["cta_seq"] if x else None, x["err"] if x else None, self.timing if x else None)
             self.launches += 4            # pair_count, pair_tile_scan, tile_negs, sgns_tile
             return stats
-        if self.world > 1 and self._xchg["variant"] == 3:
+        # pair_count, pair_tile_scan (zeroes the statistics), pair_fill, then the training kernel
+        if self.world > 1:
             x = self._xchg
             _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
                                int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
                                float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank,
                                x["xptrs"], x["fptrs"], x["cta_seq"], x["err"], self.timing, self.debug,
                                self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc, self.pg_tiles,
-                               x["mc_x"], self._share_centre, self.exp_table)
-            self.launches += 3            # + the training kernel counted below
-        elif self.world > 1:
-            x = self._xchg
-            _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
-                         int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
-                         float(cfg.max_grad), self.compute_loss, x["grid"], self.world, self.rank, x["tb"],
-                         x["slot_floats"], x["xptrs"], x["fptrs"], x["mc"], x["cta_seq"], x["err"], self.timing,
-                         self.debug, x["variant"], self.exp_table)
+                               x["mc_x"], self._share_centre, self.exp_table, self.row_scale0, self.row_scale1)
         else:
             if not hasattr(self, "_grid1"):
-                self._variant, self._grid1 = self._pick_single_kernel()
-            if self._variant == 3:
-                _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
-                                   int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
-                                   float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
-                                   None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
-                                   self.pg_tiles, 0, self._share_centre, self.exp_table)
-                self.launches += 4            # pair_count, pair_tile_scan, pair_fill, sgns_pairs
-                return stats
-            _C.sgns_step(e.syn0, e.syn1, tok, sid, self.count, self.alias_dev, stats, int(raw_pos0),
-                         int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
-                         float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, 0, 0, [], [], 0,
-                         None, None, None, self.debug, self._variant, self.exp_table)
-        self.launches += 1
+                self._grid1 = int(_C.sgns_pairs_grid(self.K, self.dev.index or 0, False))
+            _C.sgns_step_pairs(e.syn0, e.syn1, tok, sid, self.count, t, self.alias_dev, stats, int(raw_pos0),
+                               int(cfg.seed), int(iteration), cfg.window, cfg.negatives, wm, float(alpha),
+                               float(cfg.max_grad), self.compute_loss, self._grid1, 1, 0, [], [], None, None,
+                               None, self.debug, self.pg_cinfo, self.pg_off, self.pg_npairs, self.pg_desc,
+                               self.pg_tiles, 0, self._share_centre, self.exp_table, self.row_scale0,
+                               self.row_scale1)
+        self.launches += 4
         return stats
 
     def _top_k_fused(self, qs: torch.Tensor, norms: torch.Tensor, k: int, tc: bool):
@@ -434,28 +410,6 @@ class CudaShardOps:
         cos = torch.where(idx >= 0, cos, torch.full_like(cos, -3.0e38))
         sim, order = torch.sort(cos, dim=1, descending=True)
         return torch.gather(idx, 1, order)[:, :k].contiguous(), sim[:, :k].contiguous()
-
-    def _pick_single_kernel(self):
-        """single-shard kernel variant: 2 = lane-group register path, 1 = TMA pipeline, 0 = v1."""
-        cfg = self.cfg
-        dev_index = self.dev.index or 0
-        want = os.environ.get("GW2V_SINGLE_KERNEL", self.e.opts.kernel)
-        group_ok = bool(_C.sgns_group_supported(self.K, cfg.window, cfg.negatives))
-        pipe_ok = bool(_C.sgns_pipe_supported(self.K, cfg.window, cfg.negatives))
-        pairs_ok = bool(_C.sgns_pairs_supported(self.K, cfg.window, cfg.negatives))
-        if want == "auto":
-            # measured on B200 (profiles/r1_kernel_variants.md): the lane-group register path wins at every
-            # row length (TMA bulk copies cost ~25 SM cycles each, which binds the pipeline for short rows)
-            want = "pairs" if pairs_ok else ("group" if group_ok else ("pipe" if pipe_ok else "v1"))
-        if want == "pairs" and pairs_ok:
-            return 3, int(_C.sgns_pairs_grid(self.K, dev_index, False))
-        if self._share_centre:
-            raise RuntimeError('neg_sharing="centre" is implemented by the pairs kernel only')
-        if want == "group" and group_ok:
-            return 2, int(_C.sgns_group_grid(self.K, dev_index))
-        if want == "pipe" and pipe_ok:
-            return 1, int(_C.sgns_pipe_grid(self.K, cfg.negatives, dev_index))
-        return 0, int(_C.sgns_single_grid(self.K, dev_index))
 
     # ------------------------------------------------------------------ inference
     def serve(self):

@@ -289,7 +289,7 @@ def test_tile_shared_negatives_engine_equals_oracle_and_shards_agree():
 
     def make(world, rank):
         e = ShardEngine(cfg, comm=FakeComm(rank, world), device=torch.device("cpu"),
-                        options=EngineOptions(batch_size=300))
+                        options=EngineOptions(batch_size=300, hot_row_cap=0))
         e.init_weights()
         e.set_noise(counts)
         g = torch.Generator().manual_seed(1)
@@ -440,4 +440,4 @@ def test_checkpoint_pruning_never_deletes_latest_and_stale_runs_are_refused(tmp_
     from glint_word2vec_b200.parallel.comm import Comm
     with pytest.raises(ValueError, match="does not belong to this run"):
         checkpoint.resume(d, other, np.arange(v, 0, -1), Comm(), torch.device("cpu"),
-                          EngineOptions(subsample_mode="reference"))
+                          EngineOptions(subsample_mode="reference", hot_row_cap=0))

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, d, out_dir):
+def _worker(rank, world, port, d, out_dir, n=5):
     import torch.distributed as dist
     from glint_word2vec_b200.data.sampler import zipf_counts
     from glint_word2vec_b200.models import sgns
@@ -33,8 +33,8 @@ def _worker(rank, world, port, d, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         v, t = 100000, 6000
-        cfg = SGNSConfig(v, d, 5, 5, seed=11)
-        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference"))
+        cfg = SGNSConfig(v, d, 5, n, seed=11)
+        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
         eng.init_weights()
         counts = zipf_counts(v, 10 ** 7, 0.6)
         eng.set_noise(counts)
@@ -117,6 +117,21 @@ def test_fused_multi_matches_oracle(world, d, nvls, serve_fused, debug, tmp_path
     assert r["idx16"][:, 0].tolist() == list(range(100, 116))
 
 
+@pytest.mark.parametrize("world,d,n", [(2, 300, 10), (8, 300, 10), (2, 64, 16)])
+def test_fused_multi_many_negatives(world, d, n, tmp_path):
+    """More than 7 negatives per pair (BASELINE.json config 4: 80 M x 300, neg 10): split descriptors through the
+    production column-shard kernel (csrc/pairgen.cu, csrc/sgns_pairs.cu) against the dense oracle."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), d, str(tmp_path), n), nprocs=world, join=True)
+    r = torch.load(os.path.join(tmp_path, "result.pt"))
+    assert [int(x) for x in r["stats"][:, 0]] == r["pairs"]
+    upd_ref = r["ref0"] - r["start0"]
+    upd_got = r["got0"] - r["start0"]
+    assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2
+
+
 def _worker_tile(rank, world, port, d, nn, out_dir):
     import torch.distributed as dist
     from glint_word2vec_b200.data.sampler import zipf_counts
@@ -132,7 +147,7 @@ def _worker_tile(rank, world, port, d, nn, out_dir):
     try:
         v = 200000
         cfg = SGNSConfig(v, d, 5, 5, seed=11, neg_sharing="tile", tile_negatives=nn)
-        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference"))
+        eng = ShardEngine(cfg, comm=TorchDistComm(), device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
         eng.init_weights()
         eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
         full1 = (torch.rand(v, eng.shard.padded_vector_size, generator=torch.Generator().manual_seed(5)) - 0.5) * 0.5

@@ -81,24 +81,22 @@ def test_subsample_compact_matches_numpy():
 
 def _make_engine(dev, v, d, window=5, n=5, window_mode="reference", seed=7):
     cfg = SGNSConfig(v, d, window, n, seed=seed, window_mode=window_mode)
-    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
     eng.init_weights()
     counts = zipf_counts(v, 10 ** 7, 0.6)
     eng.set_noise(counts)
     return eng, counts
 
 
-@pytest.mark.parametrize("variant", ["pairs", "group", "pipe", "v1"])
 @pytest.mark.parametrize("d,window,n,wmode", [(64, 5, 5, "reference"), (100, 5, 5, "reference"),
                                               (128, 3, 7, "word2vec_c"), (512, 5, 5, "reference"),
-                                              (300, 5, 10, "word2vec_c"), (40, 5, 5, "reference")])
-def test_sgns_step_single_matches_oracle(d, window, n, wmode, variant, monkeypatch):
+                                              (300, 5, 10, "word2vec_c"), (40, 5, 5, "reference"),
+                                              (64, 4, 16, "reference"), (128, 5, 21, "reference")])
+def test_sgns_step_single_matches_oracle(d, window, n, wmode):
     """Distinct centre/context tokens and V >> negatives: concurrent warps almost never
     re-read a row another warp has just updated, so the Hogwild kernel must match the
     summed mini-batch oracle closely (sequential-vs-batch oracle runs differ by < 1e-2 here)."""
     dev = _dev()
-    # group = lane-group register path, pipe = per-warp TMA pipeline, v1 = warp-per-centre
-    monkeypatch.setenv("GW2V_SINGLE_KERNEL", variant)
     v = 200000
     eng, counts = _make_engine(dev, v, d, window, n, wmode)
     g = torch.Generator().manual_seed(0)
@@ -132,15 +130,13 @@ def test_sgns_step_single_matches_oracle(d, window, n, wmode, variant, monkeypat
     assert float(eng.syn0[:, d:].abs().sum()) == 0.0 or eng.shard.cols == d
 
 
-@pytest.mark.parametrize("variant", ["pairs", "group"])
-def test_sgns_step_sigmoid_table_mode(variant, monkeypatch):
+def test_sgns_step_sigmoid_table_mode():
     """sigmoid_mode="table": the kernels look sigma up in the reference's 1000-entry table (MLLIB:281-302,
     index scale 83.0) - diffed against the oracle in the same mode, with dots spread over [-6, 6] and beyond."""
     dev = _dev()
-    monkeypatch.setenv("GW2V_SINGLE_KERNEL", variant)
     v, d = 50000, 64
     cfg = SGNSConfig(v, d, 5, 5, seed=7, sigmoid_mode="table")
-    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
     eng.init_weights()
     eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
     g = torch.Generator().manual_seed(0)
@@ -171,7 +167,7 @@ def test_sgns_step_neg_sharing_centre_matches_oracle():
     dev = _dev()
     v, d = 200000, 64
     cfg = SGNSConfig(v, d, 5, 5, seed=7, neg_sharing="centre")
-    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
     eng.init_weights()
     eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
     g = torch.Generator().manual_seed(0)
@@ -262,6 +258,15 @@ def test_async_steps_stage_inputs_safely():
         st = h.result()
         assert int(st[0]) == len(ci)
         assert int(st[3]) == len(tok)
+
+
+def test_unsupported_shape_is_rejected_loudly():
+    """No silent fall-back kernels: shapes outside the fused step's limits raise with the limit named."""
+    dev = _dev()
+    with pytest.raises(ValueError, match="negatives <= 21"):
+        ShardEngine(SGNSConfig(1000, 64, 5, 30), device=dev)
+    with pytest.raises(ValueError, match="window <= 11"):
+        ShardEngine(SGNSConfig(1000, 64, 15, 5), device=dev)
 
 
 def test_zero_pair_step_is_noop():
@@ -398,3 +403,38 @@ def test_scores_tc_tcgen05_matches_fp32(k, q):
     # the exact CUDA-core path agrees to fp32 rounding
     out2 = C.scores_rows(syn0, qs[:8].contiguous())
     assert torch.allclose(out2, ref[:8], rtol=1e-4, atol=1e-4)
+
+
+def test_pairs_kernel_hot_row_damping_matches_oracle_with_row_scales():
+    """Hot-row damping in the pair kernel: the update of row r is scaled by the engine's table for the first H rows.
+    Checked against the oracle given the same scales, on tokens that include the hot rows."""
+    dev = _dev()
+    v, d, t = 100000, 64, 3000
+    cfg = SGNSConfig(v, d, 5, 5, seed=7)
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=4.0))
+    eng.init_weights()
+    eng.set_noise(zipf_counts(v, 10 ** 7, 1.0))
+    g = torch.Generator().manual_seed(0)
+    syn1 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    syn0 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    eng.syn0, eng.syn1 = syn0.to(dev), syn1.to(dev)
+    s0, s1 = eng.row_scales(eng.inflight_tokens(t))
+    h = s0.shape[0]
+    assert 10 < h < v and s0[0] < 0.05
+    full0, full1 = torch.ones(v), torch.ones(v)
+    full0[:h], full1[:h] = torch.from_numpy(s0), torch.from_numpy(s1)
+    rng = np.random.default_rng(1)
+    tokens = np.concatenate([np.arange(0, 400), rng.choice(np.arange(400, v), size=t - 400, replace=False)]).astype(np.int32)
+    rng.shuffle(tokens)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0.clone(), syn1.clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 5, 0, 0.002, row_scale0=full0, row_scale1=full1)
+    plain0 = syn0.clone()
+    sgns.sgns_minibatch_reference(plain0, syn1.clone(), cfg, eng.alias, tokens, sid, 5, 0, 0.002)
+    stats = eng.train_step(tokens, sid, 5, 0, 0.002).cpu()
+    assert int(stats[0]) == st.pairs
+    got0, got1 = eng.syn0.cpu(), eng.syn1.cpu()
+    r0, r1 = ref0 - syn0, ref1 - syn1
+    assert float((got0 - syn0 - r0).norm() / r0.norm()) < 2e-2
+    assert float((got1 - syn1 - r1).norm() / r1.norm()) < 2e-2
+    assert float((plain0 - syn0 - r0).norm() / r0.norm()) > 0.1          # the scales do change the update

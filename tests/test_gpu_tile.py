@@ -39,7 +39,7 @@ def test_umma_descriptor_probes():
 
 def _engine(dev, v, d, nn, window=5, n=5, wmode="reference", seed=7):
     cfg = SGNSConfig(v, d, window, n, seed=seed, window_mode=wmode, neg_sharing="tile", tile_centres=128, tile_negatives=nn)
-    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference"))
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=0))
     eng.init_weights()
     counts = zipf_counts(v, 10 ** 7, 0.6)
     eng.set_noise(counts)
@@ -212,3 +212,32 @@ def test_tile_kernel_many_tiles_per_cta(d, nn, grid, monkeypatch):
     r0, r1 = ref0 - syn0[:, :d], ref1 - syn1[:, :d]
     assert float((got0 - syn0[:, :d] - r0).norm() / r0.norm()) < 2e-2
     assert float((got1 - syn1[:, :d] - r1).norm() / r1.norm()) < 2e-2
+
+
+def test_tile_kernel_hot_row_damping_matches_oracle_with_row_scales():
+    dev = _dev()
+    v, d, nn, t = 100000, 64, 32, 3000
+    cfg = SGNSConfig(v, d, 5, 5, seed=7, neg_sharing="tile", tile_negatives=nn)
+    eng = ShardEngine(cfg, device=dev, options=EngineOptions(subsample_mode="reference", hot_row_cap=4.0))
+    eng.init_weights()
+    eng.set_noise(zipf_counts(v, 10 ** 7, 1.0))
+    g = torch.Generator().manual_seed(0)
+    syn1 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    syn0 = torch.randn(v, d, generator=g) * (0.5 / d ** 0.5)
+    eng.syn0, eng.syn1 = syn0.to(dev), syn1.to(dev)
+    s0, s1 = eng.row_scales(eng.inflight_tokens(t))
+    h = s0.shape[0]
+    full0, full1 = torch.ones(v), torch.ones(v)
+    full0[:h], full1[:h] = torch.from_numpy(s0), torch.from_numpy(s1)
+    rng = np.random.default_rng(1)
+    tokens = np.concatenate([np.arange(0, 400), rng.choice(np.arange(400, v), size=t - 400, replace=False)]).astype(np.int32)
+    rng.shuffle(tokens)
+    sid = (np.arange(t) // 37).astype(np.int32)
+    ref0, ref1 = syn0.clone(), syn1.clone()
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 5, 0, 0.002, row_scale0=full0, row_scale1=full1)
+    stats = eng.train_step(tokens, sid, 5, 0, 0.002).cpu()
+    assert int(stats[0]) == st.pairs
+    got0, got1 = eng.syn0.cpu(), eng.syn1.cpu()
+    r0, r1 = ref0 - syn0, ref1 - syn1
+    assert float((got0 - syn0 - r0).norm() / r0.norm()) < 2e-2
+    assert float((got1 - syn1 - r1).norm() / r1.norm()) < 2e-2
