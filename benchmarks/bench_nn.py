@@ -57,10 +57,14 @@ def main():
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0) * 1e9
-    for mode in ("1", "0"):
-        os.environ["GW2V_NN_TC"] = mode
+    results = {}
+    # select: row-sharded replica + score GEMM with in-epilogue selection (ops/nn.py, csrc/nn_select.cu) -- the product;
+    # dense_*: the round-1 path ([Q, V] partial scores reduce-scattered over NVLink, then top-k), kept as fallback
+    for name, sel, tcm in (("select_tcgen05", "1", "1"), ("dense_tcgen05_tf32_rerank", "0", "1"), ("dense_exact_fp32", "0", "0")):
+        os.environ["GW2V_NN_SELECT"] = sel
+        os.environ["GW2V_NN_TC"] = tcm
         for _ in range(3):
-            eng.top_k(q, args.k)
+            res = eng.top_k(q, args.k)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -75,10 +79,20 @@ def main():
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        sweep_bytes = args.vocab * eng.shard.cols * 4
-        out["tcgen05_tf32_rerank" if mode == "1" else "exact_fp32"] = {
-            "ms_per_batch": ms, "queries_per_sec": args.queries / (ms * 1e-3),
-            "hbm_fraction_of_measured_copy_bw": sweep_bytes / (ms * 1e-3) / hbm}
+        if sel == "1":
+            nn = eng._cuda.nn_index()
+            sweep_bytes = nn.rows * nn.Kp * 4 * (1.0 + 1.0 / 64)
+            extra = {"rows_per_gpu": nn.rows, "row_floats": nn.Kp, "overflows": nn.overflows}
+            results[name] = res
+        else:
+            sweep_bytes = args.vocab * eng.shard.cols * 4
+            extra = {}
+            results[name] = res
+        out[name] = dict({"ms_per_batch": ms, "queries_per_sec": args.queries / (ms * 1e-3),
+                          "hbm_fraction_of_measured_copy_bw": sweep_bytes / (ms * 1e-3) / hbm}, **extra)
+    a, b = results["select_tcgen05"], results["dense_exact_fp32"]
+    out["select_agrees_with_exact"] = {"idx_match": float((a[0] == b[0]).float().mean()),
+                                       "max_sim_diff": float((a[1] - b[1]).abs().max())}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -174,8 +174,26 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
         self._validate_for_fit()
         vocab = build_vocab_from_file(path, self.getMinCount(), tokenizer)
         log.info("vocabSize = %d, trainWordsCount = %d", vocab.size, vocab.train_words)   # MLLIB:278
-        corpus = encode_text_file(path, vocab, self.getMaxSentenceLength(), tokenizer)
-        return self._fit_encoded(vocab, corpus)
+        # Large files are never held in host memory: the native encoder streams ``<cache>/corpus.tokens.i32`` block by
+        # block, training reads it through a memory map, and shard servers receive the prefix, not the tokens.
+        # parameterServerConfig: corpus_cache_dir (kept after the fit) / stream_threshold_bytes (default 1 GiB).
+        pcfg = self.getParameterServerConfig()
+        cache = pcfg.get("corpus_cache_dir")
+        tmp = None
+        if cache is None and os.path.getsize(path) >= int(pcfg.get("stream_threshold_bytes", 1 << 30)):
+            import tempfile
+            cache = tmp = tempfile.mkdtemp(prefix="gw2v-corpus-", dir=pcfg.get("scratch_dir"))
+        if cache is None:
+            return self._fit_encoded(vocab, encode_text_file(path, vocab, self.getMaxSentenceLength(), tokenizer))
+        os.makedirs(cache, exist_ok=True)
+        try:
+            corpus = encode_text_file(path, vocab, self.getMaxSentenceLength(), tokenizer,
+                                      out_prefix=os.path.join(cache, "corpus"))
+            return self._fit_encoded(vocab, corpus)
+        finally:
+            if tmp is not None:
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
 
     def fitEncoded(self, tokens: np.ndarray, offsets: np.ndarray, counts: np.ndarray,
                    words: Optional[Sequence[str]] = None) -> ServerSideGlintWord2VecModel:

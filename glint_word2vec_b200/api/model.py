@@ -40,12 +40,23 @@ class _Writer:
         return self
 
     def save(self, path: str):
-        if os.path.exists(path):
+        """SPMD (every rank of a torchrun job calls this): the writer rank decides and removes, the others learn the
+        decision through a broadcast and wait at a barrier -- a rank that raced ahead could otherwise see the path
+        half-removed, or write its shard into a directory that rank 0 is still deleting."""
+        inst = self._instance
+        comm = getattr(getattr(inst._handle, "engine", None), "comm", None)
+        spmd = comm is not None and comm.world > 1
+        exists = os.path.exists(path) if inst._is_writer_rank() else None
+        if spmd:
+            exists = comm.broadcast_object(exists, 0)
+        if exists:
             if not self._overwrite:
                 raise IOError(f"Path {path} already exists. To overwrite it, please use write.overwrite().save(path).")
-            if self._instance._is_writer_rank():
+            if inst._is_writer_rank():
                 shutil.rmtree(path)
-        self._instance._save_impl(path)
+            if spmd:
+                comm.barrier()
+        inst._save_impl(path)
 
 
 class ServerSideGlintWord2VecModel(ServerSideGlintWord2VecBase):

@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 
 # csrc/legacy/ (the superseded round-1 kernel generations) is deliberately not part of the build
-CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu", "serve_fused.cu", "umma_probe.cu", "sgns_tile.cu"]
+CU_SOURCES = ["sgns_pairs.cu", "pairgen.cu", "prep_kernels.cu", "infer_kernels.cu", "nn_tc.cu", "nn_select.cu", "serve_fused.cu", "umma_probe.cu", "sgns_tile.cu"]
 CPP_SOURCES = ["bindings.cpp", "bindings_tile.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]

@@ -403,6 +403,93 @@ void serve_topk_owned_push(ServeCtx& c, Tensor slab_local, int64_t nsrc, int64_t
     c.wait(s);
 }
 
+// ---- nearest neighbours with in-epilogue selection (nn_select.cu) --------------------------------------------
+Tensor nn_pad_queries(Tensor qs) {
+    int qp = gw2v::scores_tc_padded_queries((int)qs.size(0));
+    auto qpad = torch::zeros({qp, qs.size(1)}, qs.options());
+    qpad.narrow(0, 0, qs.size(0)).copy_(qs);
+    return qpad;
+}
+
+// cosines of every `stride`-th row: [Q, ceil(rows / stride)] (the threshold sample)
+Tensor nn_sample_cosines(Tensor mat, Tensor inv_norm, Tensor qpad, int64_t Q, int64_t stride) {
+    CHECK_CUDA(mat); CHECK_CONTIG(mat); CHECK_CUDA(inv_norm); CHECK_CUDA(qpad); CHECK_CONTIG(qpad);
+    CHECK_DT(mat, torch::kFloat32); CHECK_DT(inv_norm, torch::kFloat32);
+    c10::cuda::CUDAGuard guard(mat.device());
+    const int64_t rows = (mat.size(0) + stride - 1) / stride;
+    auto out = torch::empty({Q, rows}, mat.options());
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    int rc = gw2v::launch_nn_select(mat.data_ptr<float>(), rows, (int)mat.size(1), stride * mat.size(1),
+                                    inv_norm.data_ptr<float>(), stride, qpad.data_ptr<float>(), (int)Q, 1,
+                                    out.data_ptr<float>(), rows, nullptr, nullptr, nullptr, 0, sms, cur_stream());
+    TORCH_CHECK(rc == 0, "nn_sample_cosines failed (rc=", rc, ")");
+    check_launch("nn_sample_cosines");
+    return out;
+}
+
+// full sweep; rows whose cosine reaches thr[q] are appended to cand[q] -> (cand int32 [Q, cap], count int32 [Q])
+std::vector<Tensor> nn_select(Tensor mat, Tensor inv_norm, Tensor qpad, int64_t Q, Tensor thr, int64_t cap) {
+    CHECK_CUDA(mat); CHECK_CONTIG(mat); CHECK_CUDA(inv_norm); CHECK_CUDA(qpad); CHECK_CONTIG(qpad); CHECK_CUDA(thr);
+    CHECK_DT(mat, torch::kFloat32); CHECK_DT(inv_norm, torch::kFloat32); CHECK_DT(thr, torch::kFloat32);
+    TORCH_CHECK(thr.numel() >= Q && inv_norm.numel() >= mat.size(0), "nn_select: thr / inv_norm too short");
+    TORCH_CHECK(mat.size(0) < (1ll << 31), "nn_select: at most 2^31 rows per shard");
+    c10::cuda::CUDAGuard guard(mat.device());
+    auto iopt = mat.options().dtype(torch::kInt32);
+    auto cand = torch::empty({Q, cap}, iopt);
+    auto count = torch::zeros({Q}, iopt);
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    int rc = gw2v::launch_nn_select(mat.data_ptr<float>(), mat.size(0), (int)mat.size(1), mat.size(1),
+                                    inv_norm.data_ptr<float>(), 1, qpad.data_ptr<float>(), (int)Q, 0, nullptr, 0,
+                                    thr.data_ptr<float>(), cand.data_ptr<int>(), count.data_ptr<int>(), (int)cap, sms,
+                                    cur_stream());
+    TORCH_CHECK(rc == 0, "nn_select failed (rc=", rc, ")");
+    check_launch("nn_select");
+    return {cand, count};
+}
+
+// exact fp32 cosines of the selected rows -> (values [Q, cap] (-3e38 beyond count), global indices int64 [Q, cap])
+std::vector<Tensor> nn_rerank(Tensor mat, Tensor inv_norm, Tensor qpad, int64_t Q, Tensor cand, Tensor count,
+                              int64_t row_base) {
+    CHECK_CUDA(mat); CHECK_CUDA(cand); CHECK_CUDA(count); CHECK_DT(cand, torch::kInt32); CHECK_DT(count, torch::kInt32);
+    c10::cuda::CUDAGuard guard(mat.device());
+    const int64_t cap = cand.size(1);
+    auto out_v = torch::empty({Q, cap}, mat.options());
+    auto out_i = torch::empty({Q, cap}, mat.options().dtype(torch::kInt64));
+    gw2v::launch_nn_rerank(mat.data_ptr<float>(), (int)mat.size(1), inv_norm.data_ptr<float>(), qpad.data_ptr<float>(),
+                           (int)Q, cand.data_ptr<int>(), count.data_ptr<int>(), (int)cap, row_base,
+                           out_v.data_ptr<float>(), reinterpret_cast<long long*>(out_i.data_ptr<int64_t>()), cur_stream());
+    check_launch("nn_rerank");
+    return {out_v, out_i};
+}
+
+// column shard -> row shards of the serving replica on every owner (in-kernel peer stores + sequence flag)
+void serve_rowshard_push(ServeCtx& c, Tensor syn0, std::vector<int64_t> replica_ptrs, int64_t vown, int64_t ldr) {
+    CHECK_CUDA(syn0); CHECK_CONTIG(syn0); CHECK_DT(syn0, torch::kFloat32);
+    c10::cuda::CUDAGuard guard(syn0.device());
+    gw2v::ServeSync s = c.next();
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    gw2v::launch_rowshard_push(syn0.data_ptr<float>(), syn0.size(0), (int)syn0.size(1), peer_ptrs(c, replica_ptrs), vown,
+                               (int)ldr, (int)(c.rank * syn0.size(1)), s, sms, cur_stream());
+    check_launch("rowshard_push");
+    c.wait(s);
+}
+
+// local top-k of a candidate list, winners pushed to every rank's [q][src][k] exchange region
+void serve_topk_cand_push(ServeCtx& c, Tensor cand_v, Tensor cand_i, int64_t k, std::vector<int64_t> candv_ptrs,
+                          std::vector<int64_t> candi_ptrs) {
+    CHECK_CUDA(cand_v); CHECK_CUDA(cand_i); CHECK_CONTIG(cand_v); CHECK_CONTIG(cand_i); CHECK_DT(cand_i, torch::kInt64);
+    c10::cuda::CUDAGuard guard(cand_v.device());
+    gw2v::ServeSync s = c.next();
+    gw2v::PeerIdx pi{};
+    TORCH_CHECK((int64_t)candi_ptrs.size() == c.world, "need one candidate-index pointer per rank");
+    for (int64_t r = 0; r < c.world; ++r) pi.p[r] = reinterpret_cast<long long*>(candi_ptrs[r]);
+    gw2v::launch_topk_merge_push(cand_v.data_ptr<float>(), reinterpret_cast<const long long*>(cand_i.data_ptr<int64_t>()),
+                                 (int)cand_v.size(1), (int)cand_v.size(0), (int)k, peer_ptrs(c, candv_ptrs), pi, s,
+                                 cur_stream());
+    check_launch("topk_cand_push");
+    c.wait(s);
+}
+
 // final merge of the world*k candidates per query (destroys cand_v)
 std::vector<Tensor> serve_topk_final(Tensor cand_v, Tensor cand_i, int64_t k) {
     CHECK_CUDA(cand_v); CHECK_CUDA(cand_i); CHECK_CONTIG(cand_v); CHECK_CONTIG(cand_i);
@@ -466,4 +553,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("cosine_topk", &cosine_topk);
     m.def("scores_tc", &scores_tc);
     m.def("scores_tc_supported", &scores_tc_supported);
+    m.def("nn_select_supported", [](int64_t K, int64_t Q) { return gw2v::nn_select_supported((int)K, (int)Q); });
+    m.def("nn_pad_queries", &nn_pad_queries);
+    m.def("nn_sample_cosines", &nn_sample_cosines);
+    m.def("nn_select", &nn_select);
+    m.def("nn_rerank", &nn_rerank);
+    m.def("serve_rowshard_push", &serve_rowshard_push);
+    m.def("serve_topk_cand_push", &serve_topk_cand_push);
 }

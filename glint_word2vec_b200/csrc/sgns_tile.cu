@@ -300,8 +300,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         }
     } else {
         // =========================================================== epilogue: group 0 = warps 0-3, group 1 = warps 4-7
-        // Epilogue 1 is split by columns (group 0: band of the context block, group 1: shared negatives); the pass-B
-        // chunks alternate between the groups with the accumulator buffer (chunk gc belongs to group gc & 1).
+        // Epilogue 1 is split by columns (each group takes half of the band window and half of the shared negatives); the
+        // pass-B chunks alternate between the groups with the accumulator buffer (chunk gc belongs to group gc & 1).
         const int grp = warp >> 2;
         const int q = warp & 3;                                          // TMEM lane quadrant
         const int row = q * 32 + lane;                                   // centre index in the tile / TMEM lane
@@ -431,10 +431,12 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             if constexpr (!MULTI) {
                 mbar_wait(s_full, it & 1, 31);
                 tc_fence_after();
-                if (grp == 0) {
+                // Both groups take half of each part (measured: with "group 0 = band, group 1 = negatives" the band group
+                // idled at the barrier below for ~12 % of the epilogue time -- 32 sigmoids against <= 10).
+                {
                     // band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
 #pragma unroll 1
-                    for (int h = 0; h < 4; ++h) {
+                    for (int h = 2 * grp; h < 2 * grp + 2; ++h) {
                         uint32_t x[16];
                         tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
                         tmem_ld_wait();
@@ -444,10 +446,11 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                             if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = __uint_as_float(x[j]);
                         }
                     }
-                } else {
+                }
+                {
                     // shared negatives: columns [160, 160 + NN)
 #pragma unroll 1
-                    for (int h = 0; h < NN / 16; ++h) {
+                    for (int h = grp * (NN / 32); h < (grp + 1) * (NN / 32); ++h) {
                         uint32_t x[16];
                         tmem_ld16(lane_addr + (uint32_t)(TL_CTX + 16 * h), x);
                         tmem_ld_wait();
@@ -488,9 +491,13 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
                     return v;
                 };
-                if (grp == 0) {
+                {
+                    // both groups take half of the band slots and half of the negatives (see the single-shard branch)
+                    constexpr int S4 = SLP / 4;
+                    constexpr int S4H = (S4 + 1) / 2;
 #pragma unroll
-                    for (int s4 = 0; s4 < SLP / 4; ++s4) {
+                    for (int s4 = 0; s4 < S4; ++s4) {
+                        if ((s4 < S4H) != (grp == 0)) continue;
                         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int src = 0; src < p.world; ++src) {
                             const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + 4 * s4);
@@ -499,9 +506,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         band_emit(4 * s4 + 0 - WM, t.x); band_emit(4 * s4 + 1 - WM, t.y);
                         band_emit(4 * s4 + 2 - WM, t.z); band_emit(4 * s4 + 3 - WM, t.w);
                     }
-                } else {
+                }
+                {
 #pragma unroll 1
-                    for (int h = 0; h < NN / 16; ++h) {
+                    for (int h = grp * (NN / 32); h < (grp + 1) * (NN / 32); ++h) {
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = 0.f;
@@ -526,7 +534,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             const bool u_on = m > 0;
             const float su = row_scale(p.row_scale0, p.hot_rows, utok);          // hot-row damping (sgns_params.h)
             const int ntok = row < NN ? (int)ldsu(sm, meta + (TL_T + TL_CTX + row) * 4) : 0;
-            const float sn = row_scale(p.row_scale1, p.hot_rows, ntok);
+            const float sn = row_scale(p.row_scale1, p.hot_rows, ntok) * p.tile_neg_scale;   // in-tile event cap
             // context rows owned by this thread: `row` and, in warp 3 of the group, also row 128 + lane
             uint32_t cm[2]; int ctok[2]; float cs[2];
 #pragma unroll

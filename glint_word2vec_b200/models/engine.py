@@ -119,12 +119,18 @@ class ShardEngine:
         self.keep_thresh: Optional[np.ndarray] = None
         self.noise_counts: Optional[np.ndarray] = None
         self._norms: Optional[torch.Tensor] = None
+        self._version = 0                    # bumped whenever syn0 may have changed (serving caches key on it)
         self._cuda = None
         if self.device.type == "cuda":
             from ..ops import cuda as _cuda_ops      # raises loudly if the extension is missing
             self._cuda = _cuda_ops.CudaShardOps(self)
 
     # ------------------------------------------------------------------ setup
+    def _touch(self):
+        """syn0 changed (or may have): drop the cached norms and every serving replica built from it."""
+        self._norms = None
+        self._version += 1
+
     @property
     def is_cuda(self) -> bool:
         return self.device.type == "cuda"
@@ -152,7 +158,7 @@ class ShardEngine:
             full0[:, self.cfg.vector_size:] = 0
             self.syn0 = full0[:, sh.rank * sh.cols:(sh.rank + 1) * sh.cols].contiguous()
             self.syn1 = torch.zeros(v, sh.cols, dtype=torch.float32)
-        self._norms = None
+        self._touch()
 
     def set_noise(self, counts: np.ndarray, use_native: bool = True):
         """Build the unigram^0.75 alias table and the sub-sampling thresholds
@@ -177,6 +183,23 @@ class ShardEngine:
             return min(int(step_tokens), 148 * self.cfg.tile_centres)      # one tile per SM in flight
         return min(int(step_tokens), 4096)                                  # resident warps x pairs of the pair kernel
 
+    def mean_pairs_per_centre(self) -> float:
+        w = self.cfg.window
+        if self.cfg.window_mode == "reference":
+            return float(np.mean([max(0, 2 * b - 1) for b in range(w)]))
+        return float(w + 1)
+
+    def tile_neg_scale(self) -> float:
+        """neg_sharing="tile": scale of the shared negatives' row updates.  One tile adds the summed, stale contributions
+        of all its centres to each shared negative row in one event of mass ``tile_centres * m * n / tile_negatives``
+        unit updates (~90 for 128 centres, 32 negatives, window 5) -- beyond ``hot_row_cap`` it is capped like a hot row
+        (measured: without this the 10 M x 512 benchmark run diverges in tile mode, max|dot| ~ 8e5)."""
+        cap = float(self.opts.hot_row_cap)
+        if cap <= 0 or self.cfg.neg_sharing != "tile":
+            return 1.0
+        mass = self.cfg.tile_centres * self.mean_pairs_per_centre() * self.cfg.negatives / self.cfg.tile_negatives
+        return float(min(1.0, cap / max(mass, 1e-30)))
+
     def row_scales(self, window_tokens: int):
         """Hot-row damping tables ``(scale0, scale1)`` (float32, length = number of hot rows H; rows >= H are 1).
 
@@ -193,11 +216,7 @@ class ShardEngine:
         f = eff / max(eff.sum(), 1.0)
         q = cnt ** 0.75
         q /= max(q.sum(), 1e-300)
-        w = self.cfg.window
-        if self.cfg.window_mode == "reference":
-            m = float(np.mean([max(0, 2 * b - 1) for b in range(w)]))
-        else:
-            m = float(w + 1)
+        m = self.mean_pairs_per_centre()
         W = float(max(1, window_tokens))
         c0 = W * f * m
         c1 = W * m * (f + self.cfg.negatives * q)
@@ -222,11 +241,11 @@ class ShardEngine:
             self.syn0 = _slice(syn0_full)
         self.syn1 = _slice(syn1_full) if syn1_full is not None else \
             torch.zeros(v, sh.cols, dtype=torch.float32, device=self.device)
-        self._norms = None
+        self._touch()
 
     def destroy(self):
         self.syn0 = self.syn1 = None
-        self._norms = None
+        self._touch()
         if self._cuda is not None:
             self._cuda.release()
 
@@ -241,7 +260,7 @@ class ShardEngine:
         """
         if self.alias is None:
             raise RuntimeError("set_noise() must be called before training")
-        self._norms = None
+        self._touch()
         if self.is_cuda and not self.unfused:
             return self._cuda.train_step(tokens, sent_id, raw_pos0, iteration, alpha)
         return self._train_step_cpu(_host_i32(tokens), _host_i32(sent_id), raw_pos0, iteration, alpha)
@@ -252,7 +271,7 @@ class ShardEngine:
         the PREVIOUS one overlap this step's kernels (``ops/cuda.py::train_step_async``)."""
         if self.alias is None:
             raise RuntimeError("set_noise() must be called before training")
-        self._norms = None
+        self._touch()
         if self.is_cuda and not self.unfused:
             return self._cuda.train_step_async(tokens, sent_id, raw_pos0, iteration, alpha)
         return _ReadyHandle(self._train_step_cpu(_host_i32(tokens), _host_i32(sent_id), raw_pos0, iteration, alpha))
@@ -456,6 +475,14 @@ class ShardEngine:
         qn = q.norm(dim=1, keepdim=True)
         q = torch.where(qn > 0, q / qn.clamp(min=1e-30), q)       # snrm2 / sscal (MLLIB:593-595)
         k = min(k, self.cfg.vocab_size)
+        if self.is_cuda:
+            # large vocabularies: row-sharded replica + score GEMM with in-epilogue selection (ops/nn.py); the dense
+            # [Q, V] path below serves small vocabularies, huge k and the (never yet seen) candidate overflow
+            nn = self._cuda.nn_index()
+            if nn.supported(q.shape[0], k):
+                res = nn.top_k(q, k)
+                if res is not None:
+                    return res[0].cpu(), res[1].cpu()
         norms = self.norms()
         if self.is_cuda:
             idx, sim = self._cuda.top_k(self._query_slice(q), norms, k)
@@ -494,4 +521,4 @@ class ShardEngine:
                 r1 = min(v, r0 + step)
                 src = torch.from_numpy(np.array(block[r0:r1, lo - col_start:hi - col_start], dtype=np.float32, order="C"))
                 target[r0:r1, lo - sh.col_start:hi - sh.col_start] = src.to(self.device)
-        self._norms = None
+        self._touch()

@@ -229,7 +229,7 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
                              pos0: int, iteration: int, alpha: float,
                              lo: int = 0, hi: Optional[int] = None,
                              row_scale0: Optional[torch.Tensor] = None,
-                             row_scale1: Optional[torch.Tensor] = None) -> StepStats:
+                             row_scale1: Optional[torch.Tensor] = None, tile_neg_scale: float = 1.0) -> StepStats:
     """One mini-batch (centres ``lo..hi`` of the step) applied in place.
 
     All dots use pre-update rows; all updates are summed (index_add), i.e. the
@@ -243,7 +243,7 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
         return stats                      # zero-pair batches are a clean no-op (Q4)
     if cfg.neg_sharing == "tile":
         return _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
-                                         row_scale0, row_scale1)
+                                         row_scale0, row_scale1, tile_neg_scale)
     pos = np.uint64(pos0) + ci.astype(np.uint64)
     neg = draw_negatives(cfg, alias, pos, slot, iteration)
     tok = tokens.astype(np.int64)
@@ -270,7 +270,7 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
 
 
 def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
-                              row_scale0=None, row_scale1=None) -> StepStats:
+                              row_scale0=None, row_scale1=None, tile_neg_scale: float = 1.0) -> StepStats:
     """neg_sharing="tile": positives per pair, negatives per (active centre, shared negative of its tile) with
     weight m_i * n / N; every dot from pre-update rows, all updates summed."""
     tok = tokens.astype(np.int64)
@@ -295,7 +295,9 @@ def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, a
     du_pos = gplus[:, None] * vc
     dvc = gplus[:, None] * u
     du_neg = torch.einsum("an,and->ad", gminus, vn)
-    dvn = gminus[:, :, None] * ua[:, None, :]
+    # tile_neg_scale < 1 (engine.tile_neg_scale): the summed update of a shared negative row is one stale event of
+    # mass sum_i m_i n / N (~90 unit updates for 128 centres, N = 32) and is capped like the hot rows
+    dvn = gminus[:, :, None] * ua[:, None, :] * float(tile_neg_scale)
     _scaled_index_add(syn0, w, du_pos, row_scale0)
     _scaled_index_add(syn0, wa, du_neg, row_scale0)
     _scaled_index_add(syn1, c, dvc, row_scale1)

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from ..data.corpus import EncodedCorpus, iter_steps
-from ..utils.tracing import nvtx_range
+from ..utils.tracing import StepTimer
 from . import sgns
 from .engine import ShardEngine
 
@@ -38,6 +38,7 @@ class TrainReport:
     seconds: float = 0.0
     final_alpha: float = 0.0
     history: List[dict] = field(default_factory=list)
+    device_ms: dict = field(default_factory=dict)     # per-phase device time {"sgns_step": {"ms": ..., "n": steps}}
 
     @property
     def pairs_per_sec(self) -> float:
@@ -86,34 +87,88 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
     last_log = 0
     mf = open(metrics_path, "a") if (metrics_path and engine.comm.rank == 0) else None
     alpha = learning_rate
+    # statistics are read back LAG steps late: resolving the newest handle would make the host wait for the step it
+    # has just queued (one host<->device round trip per step; measured 6x slower than the engine-level loop)
+    lag = 2 if engine.is_cuda else 0
+    timer = StepTimer(engine.device)
     for k in range(start_iteration, num_iterations):
         words_prev = k * train_words
         words_it = 0
-        for si, batch in enumerate(iter_steps(corpus, step_tokens)):
-            if k == start_iteration and si < start_step:
+        skip = start_step if k == start_iteration else 0
+        # steps are cut (memory-mapped token slices, sentence ids) by a background thread, PREFETCH steps ahead
+        for si, batch in enumerate(_prefetch(iter_steps(corpus, step_tokens), PREFETCH)):
+            if si < skip:
                 words_it += batch.n_words
                 continue
             alpha = sgns.learning_rate(learning_rate, words_prev + words_it, total_words)
-            with nvtx_range("sgns_step"):
+            with timer.region("sgns_step"):          # device time of the step's kernels (CUDA events) + NVTX range
                 stats = engine.train_step_async(batch.tokens, batch.sent_id, batch.raw_pos0, k, alpha)
             pending.append(stats)
             words_it += batch.n_words
             rep.steps += 1
-            if words_prev + words_it - last_log > log_every_words or len(pending) >= 64:
+            if (words_prev + words_it - last_log > log_every_words and len(pending) > lag) or len(pending) >= 64:
                 last_log = words_prev + words_it
-                _drain(pending, rep, alpha, words_prev + words_it, mf, engine, t0)
+                ready = pending[:len(pending) - lag]
+                del pending[:len(pending) - lag]
+                _drain(ready, rep, alpha, words_prev + words_it, mf, engine, t0, timer.poll())
             if checkpoint_fn is not None:
                 checkpoint_fn(k, si + 1)
         rep.iterations += 1
         rep.words += words_it
-    _drain(pending, rep, alpha, rep.words, mf, engine, t0)
+    _drain(pending, rep, alpha, rep.words, mf, engine, t0, timer.flush())
     if engine.is_cuda:
         torch.cuda.synchronize(engine.device)
     rep.seconds = time.time() - t0
+    rep.device_ms = timer.flush()
     rep.final_alpha = alpha
     if mf:
         mf.close()
     return rep
+
+
+PREFETCH = 4
+
+
+def _prefetch(it, depth: int):
+    """Run iterator ``it`` in a daemon thread, ``depth`` items ahead (numpy slicing, memmap page faults and
+    ``np.repeat`` release the GIL, so the producer overlaps the launch loop).  Exceptions re-raise in the consumer;
+    an abandoned consumer stops the producer at its next hand-over."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+    done = object()
+    stop = threading.Event()
+
+    def put(x):
+        while not stop.is_set():
+            try:
+                q.put(x, timeout=0.2)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def run():
+        try:
+            for x in it:
+                if not put(x):
+                    return
+            put(done)
+        except BaseException as exc:          # noqa: BLE001 - handed to the consumer
+            put(exc)
+
+    th = threading.Thread(target=run, name="gw2v-steps", daemon=True)
+    th.start()
+    try:
+        while True:
+            x = q.get()
+            if x is done:
+                return
+            if isinstance(x, BaseException):
+                raise x
+            yield x
+    finally:
+        stop.set()
 
 
 def _exposed_wait_ns(engine) -> Optional[int]:
@@ -124,7 +179,7 @@ def _exposed_wait_ns(engine) -> Optional[int]:
     return int(timing[0].item())
 
 
-def _drain(pending, rep: TrainReport, alpha, words, mf, engine=None, t0=None):
+def _drain(pending, rep: TrainReport, alpha, words, mf, engine=None, t0=None, phases=None):
     if not pending:
         return
     vals = [p.result() if hasattr(p, "result") else p for p in pending]      # async step handles
@@ -145,6 +200,9 @@ def _drain(pending, rep: TrainReport, alpha, words, mf, engine=None, t0=None):
     if t0 is not None:                                   # throughput next to the loss probe
         rec["elapsed_s"] = time.time() - t0
         rec["pairs_per_sec"] = rep.pairs / rec["elapsed_s"] if rec["elapsed_s"] > 0 else None
+    if phases:                                           # cumulative device time per phase (utils/tracing.py::StepTimer)
+        rec["device_ms"] = {k: round(v["ms"], 3) for k, v in phases.items()}
+        rec["device_steps"] = {k: v["n"] for k, v in phases.items()}
     wait = _exposed_wait_ns(engine)
     if wait is not None:                                 # in-kernel time spent polling for the peers' partial dots
         rec["exposed_allreduce_wait_ns_total"] = wait

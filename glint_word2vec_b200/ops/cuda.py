@@ -122,6 +122,7 @@ class CudaShardOps:
         # back to kernel + NCCL collective (kept for A/B measurements)
         self.serve_fused = engine.comm.world > 1 and os.environ.get("GW2V_SERVE_FUSED", "1") != "0"
         self._serve = None
+        self._nn = None
 
     # ------------------------------------------------------------------ setup
     def init_weights(self, seed: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -141,6 +142,9 @@ class CudaShardOps:
     def release(self):
         self._xchg = None
         self._serve = None
+        if self._nn is not None:
+            self._nn.release()
+        self._nn = None
         self.alias_dev = self.keep_dev = None
         self._cap = 0
 
@@ -357,6 +361,7 @@ class CudaShardOps:
         wm = WINDOW_MODES[cfg.window_mode]
         if self._tile_mode:
             if not hasattr(self, "_tile_grid"):
+                self._tile_neg_scale = float(e.tile_neg_scale())
                 self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
             if self.world > 1 and self._xchg is None:
                 self._setup_tile_exchange()
@@ -367,7 +372,8 @@ class CudaShardOps:
                               self.pg_off, self.pg_npairs, self.pg_tiles, self.tile_negs, cfg.tile_negatives,
                               self.exp_table, self.row_scale0, self.row_scale1, self.tile_dbg,
                               self.world, self.rank, x["xptrs"] if x else [], x["fptrs"] if x else [],
-                              x["cta_seq"] if x else None, x["err"] if x else None, self.timing if x else None)
+                              x["cta_seq"] if x else None, x["err"] if x else None, self.timing if x else None,
+                              self._tile_neg_scale)
             self.launches += 4            # pair_count, pair_tile_scan, tile_negs, sgns_tile
             return stats
         # pair_count, pair_tile_scan (zeroes the statistics), pair_fill, then the training kernel
@@ -418,6 +424,13 @@ class CudaShardOps:
             from .serving import ServeExchange
             self._serve = ServeExchange(self)
         return self._serve
+
+    def nn_index(self):
+        """Lazily built nearest-neighbour index (row-sharded replica + fused select kernel, ops/nn.py)."""
+        if self._nn is None:
+            from .nn import NNIndex
+            self._nn = NNIndex(self)
+        return self._nn
 
     def _rows_dev(self, rows: torch.Tensor) -> torch.Tensor:
         return rows.to(self.dev, torch.int64).contiguous()

@@ -119,7 +119,7 @@ class InProcessHandle(MatrixHandle):
         rep = run_training(self.engine, corpus, lr, iters, train_words, metrics_path, train_opts)
         self.last_report = {k: getattr(rep, k) for k in
                             ("iterations", "steps", "words", "pairs", "loss_per_pair", "max_abs_dot",
-                             "seconds", "final_alpha")}
+                             "seconds", "final_alpha", "device_ms")}
         self.last_report["history"] = rep.history[-50:]
         return self.last_report
 

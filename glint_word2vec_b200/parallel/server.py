@@ -133,7 +133,7 @@ class ShardServer:
             self._path(train_opts["checkpoint_dir"])
         rep = run_training(eng, enc, float(lr), int(iters), int(train_words), self._path(metrics_path), train_opts)
         out = {k: getattr(rep, k) for k in ("iterations", "steps", "words", "pairs", "loss_per_pair",
-                                             "max_abs_dot", "seconds", "final_alpha")}
+                                             "max_abs_dot", "seconds", "final_alpha", "device_ms")}
         out["history"] = rep.history[-50:]
         self.reports[mid] = out
         return out

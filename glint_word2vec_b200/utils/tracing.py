@@ -54,6 +54,15 @@ class StepTimer:
             self.totals_ms[label] += (time.perf_counter() - t0) * 1e3
             self.counts[label] += 1
 
+    def poll(self):
+        """Harvest the regions whose end event has completed, without synchronising (safe inside a launch loop)."""
+        if self.cuda:
+            while self._pending and self._pending[0][2].query():
+                label, e0, e1 = self._pending.pop(0)
+                self.totals_ms[label] += e0.elapsed_time(e1)
+                self.counts[label] += 1
+        return {k: {"ms": v, "n": self.counts[k]} for k, v in self.totals_ms.items()}
+
     def flush(self):
         if self.cuda and self._pending:
             torch.cuda.synchronize(self.device)

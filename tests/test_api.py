@@ -269,14 +269,22 @@ def test_fit_text_file_equals_fit_on_sentences(tmp_path):
               parameterServerConfig={"device": "cpu"})
     m1 = ServerSideGlintWord2Vec(**kw).fitTextFile(str(path))
     m2 = ServerSideGlintWord2Vec(**kw).fit(sentences)
+    # streaming mode: the encoded corpus goes to disk block by block and is trained from a memory map
+    kw3 = dict(kw, parameterServerConfig={"device": "cpu", "corpus_cache_dir": str(tmp_path / "cache")})
+    m3 = ServerSideGlintWord2Vec(**kw3).fitTextFile(str(path))
+    kw4 = dict(kw, parameterServerConfig={"device": "cpu", "stream_threshold_bytes": 0, "scratch_dir": str(tmp_path)})
+    m4 = ServerSideGlintWord2Vec(**kw4).fitTextFile(str(path))
     try:
         assert m1.numWords == m2.numWords
-        v1, v2 = m1.getVectorsMap(), m2.getVectorsMap()
-        assert v1.keys() == v2.keys()
+        v1, v2, v3, v4 = m1.getVectorsMap(), m2.getVectorsMap(), m3.getVectorsMap(), m4.getVectorsMap()
+        assert v1.keys() == v2.keys() == v3.keys()
         assert all(np.array_equal(v1[w], v2[w]) for w in list(v1)[:50])
+        assert all(np.array_equal(v1[w], v3[w]) and np.array_equal(v1[w], v4[w]) for w in list(v1)[:50])
+        assert (tmp_path / "cache" / "corpus.tokens.i32").exists()                 # explicit cache dir is kept
+        assert not [p for p in tmp_path.iterdir() if p.name.startswith("gw2v-corpus-")]   # temporary one is removed
     finally:
-        m1.stop()
-        m2.stop()
+        for m in (m1, m2, m3, m4):
+            m.stop()
 
 
 def test_tile_shared_negatives_keeps_the_quality_gates():

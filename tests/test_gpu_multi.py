@@ -201,3 +201,52 @@ def test_tile_kernel_column_shards_match_oracle(world, d, nn, tmp_path):
     upd_got = r["got0"] - r["start0"]
     assert upd_ref.norm() > 0
     assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2
+
+
+def _worker_nn(rank, world, port, d, out_dir):
+    import torch.distributed as dist
+    from glint_word2vec_b200.models.engine import EngineOptions, ShardEngine
+    from glint_word2vec_b200.models.sgns import SGNSConfig
+    from glint_word2vec_b200.parallel.comm import TorchDistComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        v = 140000 * world + 77
+        eng = ShardEngine(SGNSConfig(v, d, 5, 5, seed=11), comm=TorchDistComm(), device=dev,
+                          options=EngineOptions(hot_row_cap=0))
+        eng.init_weights()
+        eng.syn0 = (eng.syn0 * d).contiguous()
+        eng._touch()
+        full = eng.pull(torch.arange(0, v, 997)).cpu()                 # sanity rows through the column path
+        g = torch.Generator().manual_seed(4)
+        qs = torch.randn(40, d, generator=g)
+        qs[:8] = full[:8] + 0.1 * torch.randn(8, d, generator=g)
+        idx, sim = eng.top_k(qs, 10)
+        nn = eng._cuda.nn_index()
+        used = nn.version == eng._version and nn.overflows == 0
+        # dense path as the oracle (GW2V_NN_SELECT=0 switches the select path off)
+        os.environ["GW2V_NN_SELECT"] = "0"
+        idx0, sim0 = eng.top_k(qs, 10)
+        if rank == 0:
+            torch.save({"idx": idx, "sim": sim, "idx0": idx0, "sim0": sim0, "used": used},
+                       os.path.join(out_dir, "nn.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d", [(2, 128), (2, 300), (4, 512), (8, 300)])
+def test_nn_row_shard_replica_matches_dense_path(world, d, tmp_path):
+    """findSynonyms over column shards: the row-sharded serving replica + fused select kernel (ops/nn.py) returns
+    the same neighbours as the dense reduce-scatter path."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_nn, args=(world, _free_port(), d, str(tmp_path)), nprocs=world, join=True)
+    r = torch.load(os.path.join(tmp_path, "nn.pt"))
+    assert r["used"]
+    assert torch.allclose(r["sim"], r["sim0"], atol=2e-5)
+    assert (r["idx"] == r["idx0"]).float().mean() > 0.97

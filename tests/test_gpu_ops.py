@@ -438,3 +438,50 @@ def test_pairs_kernel_hot_row_damping_matches_oracle_with_row_scales():
     assert float((got0 - syn0 - r0).norm() / r0.norm()) < 2e-2
     assert float((got1 - syn1 - r1).norm() / r1.norm()) < 2e-2
     assert float((plain0 - syn0 - r0).norm() / r0.norm()) > 0.1          # the scales do change the update
+
+
+@pytest.mark.parametrize("d,nq,k", [(64, 1, 10), (64, 64, 10), (100, 17, 5), (300, 64, 40), (128, 200, 1)])
+def test_nn_select_matches_exact_topk(d, nq, k):
+    """Fused select path (csrc/nn_select.cu + ops/nn.py): tcgen05 screening with in-epilogue threshold selection,
+    exact fp32 re-score -- against a dense fp32 cosine top-k.  d = 100 / 300: rows are zero-padded to 32 floats."""
+    dev = _dev()
+    v = 300000
+    eng = ShardEngine(SGNSConfig(v, d, 5, 5, seed=3), device=dev, options=EngineOptions(hot_row_cap=0))
+    eng.init_weights()
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(v, eng.shard.cols, generator=g)
+    w[:, d:] = 0
+    w[7] = 0                                   # a zero row scores 0, like the reference
+    w[1000:1010] = w[5] * torch.linspace(0.5, 2.0, 10)[:, None]     # exact cosine ties with row 5
+    eng.syn0 = w.to(dev)
+    eng._touch()
+    qs = torch.cat([w[:nq // 2 + 1, :d] + 0.3 * torch.randn(nq // 2 + 1, d, generator=g),
+                    torch.randn(nq - nq // 2 - 1, d, generator=g)])[:nq]
+    idx, sim = eng.top_k(qs, k)
+    nn = eng._cuda.nn_index()
+    assert nn.version == eng._version and nn.overflows == 0      # the select path answered
+    wn = w[:, :d].to(dev)
+    cos = (qs.to(dev) / qs.to(dev).norm(dim=1, keepdim=True)) @ (wn / wn.norm(dim=1, keepdim=True).clamp(min=1e-30)).t()
+    want_sim, want_idx = torch.topk(cos, k, dim=1)
+    assert torch.allclose(sim, want_sim.cpu(), atol=3e-6)
+    # index sets agree except where neighbouring cosines tie within fp32 noise
+    same = [(len(set(a.tolist()) & set(b.tolist()))) for a, b in zip(idx, want_idx.cpu())]
+    assert min(same) >= k - 1 and sum(same) >= nq * k - max(2, nq // 8)
+    # training invalidates the index
+    eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
+    eng.train_step(np.arange(1000, dtype=np.int32), np.zeros(1000, np.int32), 0, 0, 0.025)
+    eng.top_k(qs[:1], k)
+    assert nn.version == eng._version
+
+
+def test_nn_select_overflow_falls_back_to_dense():
+    """All rows identical: every cosine passes the threshold, the candidate lists overflow, the dense path answers."""
+    dev = _dev()
+    v, d = 300000, 64
+    eng = ShardEngine(SGNSConfig(v, d, 5, 5, seed=3), device=dev, options=EngineOptions(hot_row_cap=0))
+    eng.init_weights()
+    eng.syn0 = torch.ones(v, d, device=dev)
+    eng._touch()
+    idx, sim = eng.top_k(torch.ones(2, d), 5)
+    assert eng._cuda.nn_index().overflows == 1
+    assert torch.allclose(sim, torch.ones(2, 5), atol=1e-5)

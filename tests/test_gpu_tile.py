@@ -234,7 +234,9 @@ def test_tile_kernel_hot_row_damping_matches_oracle_with_row_scales():
     rng.shuffle(tokens)
     sid = (np.arange(t) // 37).astype(np.int32)
     ref0, ref1 = syn0.clone(), syn1.clone()
-    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 5, 0, 0.002, row_scale0=full0, row_scale1=full1)
+    assert 0.0 < eng.tile_neg_scale() < 0.1            # 128 centres x 4 pairs x 5 / 32 = 80 unit updates per event, cap 4
+    st = sgns.sgns_minibatch_reference(ref0, ref1, cfg, eng.alias, tokens, sid, 5, 0, 0.002, row_scale0=full0, row_scale1=full1,
+                                       tile_neg_scale=eng.tile_neg_scale())
     stats = eng.train_step(tokens, sid, 5, 0, 0.002).cpu()
     assert int(stats[0]) == st.pairs
     got0, got1 = eng.syn0.cpu(), eng.syn1.cpu()
