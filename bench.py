@@ -54,7 +54,7 @@ def parse():
                     help="word2vec = the intended formula of MLLIB:375-377 at --subsample-ratio; reference = the "
                          "reference's effective behaviour (integer-division bug: nothing is dropped)")
     ap.add_argument("--subsample-ratio", type=float, default=1e-4)
-    ap.add_argument("--tile-negatives", type=int, default=32, help="shared negatives per 128-centre tile (tile mode)")
+    ap.add_argument("--tile-negatives", type=int, default=64, help="shared negatives per 128-centre tile (tile mode)")
     ap.add_argument("--neg-sharing", default="pair", choices=["pair", "centre", "tile"],
                     help="semantics of the HEADLINE value: pair = n private negatives per pair (reference)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -352,11 +352,21 @@ def main():
                                           subsampleRatio=args.subsample_ratio, numParameterServers=world,
                                           parameterServerConfig={"subsample_mode": args.subsample, "step_tokens": B,
                                                                  "neg_sharing": args.neg_sharing})
+            est.setMaxIter(5)                       # 5 passes over 2K steps of tokens = 10K steps inside the clock
             model = est.fitEncoded(toks, offs, counts)
             rep = model.trainingReport
             model.stop()
-            result["e2e_fit"] = {"value": rep["pairs"] / rep["seconds"], "unit": "pairs/s", "steps": rep["steps"],
+            # steady state: the metrics records (one per drained step) after the first pass; the whole-run figure
+            # (first step = lazy CUDA module load, allocator warm-up) is reported next to it
+            hist = [h for h in rep["history"] if h.get("elapsed_s")]
+            steady = None
+            if len(hist) >= 10:
+                a, b = hist[len(hist) // 5], hist[-1]
+                steady = sum(h["pairs"] for h in hist[len(hist) // 5 + 1:]) / max(b["elapsed_s"] - a["elapsed_s"], 1e-9)
+            result["e2e_fit"] = {"value": steady if steady else rep["pairs"] / rep["seconds"], "unit": "pairs/s",
+                                 "whole_run_value": rep["pairs"] / rep["seconds"], "steps": rep["steps"],
                                  "seconds": rep["seconds"], "loss_per_pair": rep["loss_per_pair"],
+                                 "device_ms": rep.get("device_ms"),
                                  "api": "ServerSideGlintWord2Vec.fitEncoded (vocabulary, noise table, engine set-up "
                                         "outside; the training loop with per-step H2D + statistics D2H inside the clock)"}
         except Exception as e:

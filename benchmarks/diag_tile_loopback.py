@@ -47,7 +47,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         one(*[int(a) for a in sys.argv[1:7]])
     else:
-        cases = [(1, 128, 32, 3000, 4, 1), (1, 128, 64, 3000, 4, 1), (1, 128, 64, 3000, 12, 3), (8, 128, 64, 3000, 4, 3), (1, 512, 64, 3000, 2, 1), (1, 512, 64, 40000, 0, 2), (4, 100, 32, 40000, 0, 2), (1, 300, 64, 9000, 3, 2)]
+        cases = [(1, 512, 32, 40000, 0, 2), (1, 512, 32, 3000, 2, 1), (1, 256, 32, 20000, 8, 2), (1, 128, 32, 3000, 4, 1), (1, 128, 64, 3000, 4, 1), (1, 128, 64, 3000, 12, 3), (8, 128, 64, 3000, 4, 3), (1, 512, 64, 3000, 2, 1), (1, 512, 64, 40000, 0, 2), (4, 100, 32, 40000, 0, 2), (1, 300, 64, 9000, 3, 2)]
         for c in cases:
             r = subprocess.run([sys.executable, os.path.abspath(__file__)] + [str(x) for x in c], capture_output=True, text=True, timeout=300)
             out = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]

@@ -32,6 +32,10 @@ _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "kernel",
                 "tile_negatives", "device", "hot_row_cap", "sampler")
 
 
+# keys of parameterServerConfig that configure the model spec (SGNSConfig) or the placement, not EngineOptions
+_CONFIG_KEYS = ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres", "tile_negatives", "device")
+
+
 def engine_options_from_params(p: ServerSideGlintWord2VecBase) -> dict:
     """Engine options = ``parameterServerConfig`` pass-through + the ML params
     that the Glint servers receive through ``Word2VecArguments`` (MLLIB:351)."""
@@ -61,8 +65,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
     """PS bootstrap (C9): separate cluster if a host is given, SPMD if this
     process is one rank of a torchrun job, in-process for one shard, else spawn
     an integrated shard-server group."""
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                                                        "tile_negatives", "device", "hot_row_cap", "sampler")}
+    engine_opts = {k: v for k, v in opts.items() if k not in _CONFIG_KEYS}
     if host:
         h = _cluster.connect_separate(host)
         return h.create(cfg, engine_opts, counts)
@@ -81,8 +84,7 @@ def open_handle_for_fit(cfg: SGNSConfig, counts, host: str, num_servers: int, op
 
 
 def open_handle_for_load(path: str, host: str, num_servers: int, opts: dict):
-    engine_opts = {k: v for k, v in opts.items() if k not in ("window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                                                        "tile_negatives", "device", "hot_row_cap", "sampler")}
+    engine_opts = {k: v for k, v in opts.items() if k not in _CONFIG_KEYS}
     if host:
         h = _cluster.connect_separate(host)
         h.load(path, engine_opts)
@@ -218,7 +220,7 @@ class ServerSideGlintWord2Vec(ServerSideGlintWord2VecBase):
                          max_grad=float(pcfg.get("max_grad", 0.0)),
                          neg_sharing=pcfg.get("neg_sharing", "pair"),
                          tile_centres=int(pcfg.get("tile_centres", 128)),
-                         tile_negatives=int(pcfg.get("tile_negatives", 32)))
+                         tile_negatives=int(pcfg.get("tile_negatives", 64)))
         opts = engine_options_from_params(self)
         handle = open_handle_for_fit(cfg, vocab.counts, self.getParameterServerHost(),
                                      self.getNumParameterServers(), opts)

@@ -105,6 +105,20 @@ void sgns_step_pairs(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Te
     check_launch("sgns_step_pairs");
 }
 
+// hammer the 16-byte chunk pattern of the pair exchange across all peers; returns [torn, observed] (collective launch)
+Tensor xchg_selftest(std::vector<int64_t> buf_ptrs, int64_t rank, int64_t iters, Tensor result) {
+    CHECK_CUDA(result); CHECK_DT(result, torch::kInt64);
+    TORCH_CHECK((int64_t)buf_ptrs.size() <= gw2v::MAX_WORLD && result.numel() >= 2, "xchg_selftest: bad arguments");
+    c10::cuda::CUDAGuard guard(result.device());
+    gw2v::PeerTest t{};
+    t.world = (int)buf_ptrs.size(); t.rank = (int)rank; t.iters = (int)iters;
+    for (int r = 0; r < t.world; ++r) t.buf[r] = reinterpret_cast<uint32_t*>(buf_ptrs[r]);
+    t.result = reinterpret_cast<unsigned long long*>(result.data_ptr<int64_t>());
+    gw2v::launch_xchg_selftest(t, cur_stream());
+    check_launch("xchg_selftest");
+    return result;
+}
+
 void subsample_compact(Tensor tok_in, Tensor sid_in, int64_t T, Tensor keep_thresh, int64_t seed,
                        int64_t iteration, int64_t raw_pos0, Tensor tok_out, Tensor sid_out, Tensor count_out,
                        Tensor tile_ws) {
@@ -537,6 +551,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgns_pairs_grid", [](int64_t K, int64_t dev, bool multi) {
         c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
         return (int64_t)gw2v::sgns_pairs_grid((int)K, (int)dev, multi); });
+    m.def("xchg_selftest", &xchg_selftest);
     m.def("sgns_pairs_multi_geometry", []() {
         int w, ns, sf; gw2v::sgns_pairs_multi_geometry(&w, &ns, &sf); return std::vector<int64_t>{w, ns, sf}; });
     m.def("pairgen_max_blocks", [](int64_t t) { return (int64_t)gw2v::pairgen_max_blocks((int)t); });

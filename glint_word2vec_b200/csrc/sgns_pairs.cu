@@ -32,7 +32,15 @@ constexpr int PK_BATCH = 4;           // pairs per batch: slot = 32 floats = 128
 constexpr int PK_LAG = 16;            // max pairs between pass A and pass B (template parameter LAG: 4 or 16)
 constexpr int PK_NSLOT = 14;          // >= 2 * (batches in flight + 1)
 constexpr int PK_XCHUNKS = 11;        // 16-byte chunks {f, f, f, tag} carrying one batch (4 pairs x 8 dots = 32 floats)
-constexpr int PK_XSTRIDE = 48;        // floats per (slot, source) region: 12 chunks, 192 B
+constexpr int PK_XSTRIDE = 64;        // floats per (slot, source) region: 16 chunks, 256 B (the tagged-word format needs 16)
+// Exchange formats (debug bit 32 selects the second):
+//   fast  {f, f, f, tag} per 16-byte st.v4.f32 / ld.v4.u32.  Relies on an aligned 16-byte access being performed as ONE
+//         transaction end to end (SM -> NVLink -> L2 -> SM); that is how the hardware behaves, but the PTX memory model
+//         only promises single-copy atomicity up to 64 bits, so the engine runs xchg_selftest_kernel over every peer
+//         pair at start-up and switches to the tagged-word format if it ever observes a torn chunk.
+//   safe  {(f, tag), (f, tag)} per 16-byte st.v2.b64 / ld.v2.b64: every 64-bit element carries its own tag and is
+//         single-copy atomic by the memory model; 16 chunks per batch instead of 11.
+constexpr int PK_XCHUNKS_SAFE = 16;
 
 template <int G> __device__ __forceinline__ int pk_row_of_lane(int lane) {
     const int lg = lane & (G - 1);
@@ -349,11 +357,24 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                     const uint32_t h = ((uint32_t)gwarp * 2654435761u) ^ (bseq * 40503u) ^ ((uint32_t)rank * 0x9E3779B9u);
                     __nanosleep((h >> 9) & 0x3FFFu);
                 }
-                if (lane < PK_XCHUNKS) {
+                if (p.debug & 32) {
+                    if (lane < PK_XCHUNKS_SAFE) {
+                        const float* src = fdot + (size_t)((b * BS) % RFS) * P * PK_FP + 2 * lane;
+                        const unsigned long long tg = (unsigned long long)(bseq + 1u) << 32;
+                        const unsigned long long w0 = tg | (unsigned long long)__float_as_uint(src[0]);
+                        const unsigned long long w1 = tg | (unsigned long long)__float_as_uint(src[1]);
+                        for (int r = 0; r < S; ++r) {
+                            if (r == rank) continue;
+                            const int srcidx = (p.debug & 8) ? r : rank;
+                            float* dst = p.xbuf[r] + warp_x_base + ((size_t)slot * S + srcidx) * slot_stride + 4 * lane;
+                            asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+                        }
+                    }
+                } else if (lane < PK_XCHUNKS) {
                     const float* src = fdot + (size_t)((b * BS) % RFS) * P * PK_FP + 3 * lane;
                     const float x0 = src[0], x1 = src[1], x2 = (3 * lane + 2 < 32) ? src[2] : 0.f;
                     const uint32_t tag = bseq + 1u;
-                    if (p.xbuf_mc != nullptr) {
+                    if (p.xbuf_mc != nullptr) {                          // (fast format only; the engine never combines it with bit 32)
                         // NVLS: one multicast store lands in every rank's slot (switch-replicated)
                         float* dst = p.xbuf_mc + warp_x_base + ((size_t)slot * S + rank) * slot_stride + 4 * lane;
                         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -383,6 +404,31 @@ sgns_pairs_multi_kernel(const SgnsParams p, const int* __restrict__ desc, const 
                 {
                     const uint32_t tag = bseq + 1u;
                     unsigned long long t0 = p.timing ? globaltimer_ns() : 0ull;
+                    if (p.debug & 32) {
+                        // tagged-word format: (S-1) sources x 16 chunks of two (value, tag) words
+                        for (int it = lane; it < (S - 1) * PK_XCHUNKS_SAFE; it += 32) {
+                            const int q = it / PK_XCHUNKS_SAFE, c = it - q * PK_XCHUNKS_SAFE;
+                            const int srcr = q + (q >= rank ? 1 : 0);
+                            const float* ptr = p.xbuf[rank] + warp_x_base + ((size_t)slot * S + srcr) * slot_stride + 4 * c;
+                            unsigned long long w0, w1;
+                            uint32_t spins = 0;
+                            unsigned long long tw = 0ull;
+                            while (true) {
+                                asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(ptr) : "memory");
+                                if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+                                if ((++spins & 0x3FFFu) == 0) {
+                                    if (tw == 0ull) tw = globaltimer_ns();
+                                    if (globaltimer_ns() - tw > 20000000000ull) {
+                                        printf("[gw2v] rank %d warp %d: timeout waiting for rank %d batch %u\n", rank, gwarp, srcr, tag);
+                                        atomicExch(p.error_flag, 1);
+                                        __trap();
+                                    }
+                                }
+                            }
+                            xsum[srcr * 32 + 2 * c] = __uint_as_float((uint32_t)w0);
+                            xsum[srcr * 32 + 2 * c + 1] = __uint_as_float((uint32_t)w1);
+                        }
+                    } else
                     // (S-1) sources x 11 chunks, strided over the lanes; each chunk is polled until its tag matches
                     for (int it = lane; it < (S - 1) * PK_XCHUNKS; it += 32) {
                         const int q = it / PK_XCHUNKS, c = it - q * PK_XCHUNKS;
@@ -550,6 +596,44 @@ int sgns_pairs_grid(int K, int device, bool multi) {
     }
     if (occ < 1) occ = 1;
     return sms * occ;               // multi: every CTA co-resident, required by the in-kernel flag protocol
+}
+
+// Start-up self-test of the fast exchange format (see PK_XSTRIDE): block 0 of every rank streams `iters` chunks
+// {i, i, i, i} into each peer's test slot with the same st.relaxed.sys.v4 the training kernel uses, blocks 1.. poll
+// their own slots (one warp per source) with the same ld.relaxed.sys.v4 and count every observation whose four words
+// differ.  All ranks run it concurrently; result[0] = torn observations, result[1] = chunks observed.
+__global__ void xchg_selftest_kernel(PeerTest t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0) {
+        // sender: warp w -> peer w; lanes write 32 different chunks so that many 16-byte stores are in flight
+        for (int r = warp; r < t.world; r += blockDim.x / 32) {
+            if (r == t.rank) continue;
+            uint32_t* dst = t.buf[r] + ((size_t)t.rank * 32 + lane) * 4;
+            for (uint32_t i = 1; i <= (uint32_t)t.iters; ++i)
+                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(dst), "r"(i) : "memory");
+        }
+    } else {
+        for (int src = warp; src < t.world; src += blockDim.x / 32) {
+            if (src == t.rank) continue;
+            const uint32_t* ptr = t.buf[t.rank] + ((size_t)src * 32 + lane) * 4;
+            unsigned long long torn = 0, seen = 0;
+            const unsigned long long t0 = globaltimer_ns();
+            while (true) {
+                uint32_t a, b, c, d;
+                asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(ptr) : "memory");
+                ++seen;
+                if (a != b || b != c || c != d) ++torn;
+                if (a == (uint32_t)t.iters && b == a && c == a && d == a) break;
+                if ((seen & 0xFFFu) == 0 && globaltimer_ns() - t0 > 5000000000ull) { torn |= 1ull << 62; break; }   // peer never finished
+            }
+            atomicAdd(t.result, torn);
+            atomicAdd(t.result + 1, seen);
+        }
+    }
+}
+
+void launch_xchg_selftest(const PeerTest& t, cudaStream_t stream) {
+    xchg_selftest_kernel<<<2, 256, 0, stream>>>(t);
 }
 
 void sgns_pairs_multi_geometry(int* warps_per_cta, int* nslot, int* slot_floats) {

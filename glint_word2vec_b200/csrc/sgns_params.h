@@ -46,6 +46,14 @@ struct SgnsParams {
     unsigned long long* timing;  // optional [grid*2]: accumulated wait ns, tiles (exposed all-reduce time)
 };
 
+// start-up self-test of the 16-byte exchange chunks (sgns_pairs.cu)
+struct PeerTest {
+    uint32_t* buf[MAX_WORLD];     // per rank: [world][32] chunks of 16 bytes (symmetric)
+    unsigned long long* result;   // [2] torn observations, observations
+    int world, rank, iters;
+};
+void launch_xchg_selftest(const PeerTest& t, cudaStream_t stream);
+
 // sgns_pairs.cu: production step over pre-generated pair descriptors (pairgen.cu)
 bool sgns_pairs_supported(int K, int window, int negatives);
 int sgns_pairs_grid(int K, int device, bool multi);

@@ -48,7 +48,7 @@ class SGNSConfig:
     # (docs/round2_tile_gemm.md); implemented by the oracle and the un-fused library path, not yet by a kernel.
     neg_sharing: str = "pair"
     tile_centres: int = 128
-    tile_negatives: int = 32
+    tile_negatives: int = 64         # 64: half the per-tile event mass of 32 and twice the distinct negatives per token (profiles/r2_tile_kernel.md)
 
     def __post_init__(self):
         if self.neg_sharing not in ("pair", "centre", "tile"):

@@ -82,6 +82,9 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
     train_words = n_tok if train_words is None else train_words
     total_words = num_iterations * train_words
     step_tokens = auto_step_tokens(engine, n_tok)
+    if engine.is_cuda and not engine.unfused:
+        engine._cuda.prepare(min(step_tokens, max(1, n_tok)))      # buffers, damping tables, exchange rings: not per-step work
+        torch.cuda.synchronize(engine.device)
     t0 = time.time()
     pending = []
     last_log = 0

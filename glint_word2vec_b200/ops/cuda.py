@@ -211,15 +211,45 @@ class CudaShardOps:
             if int(g[0].item()) != grid or int(-g[1].item()) != grid:
                 raise RuntimeError("ranks disagree on the persistent grid size; heterogeneous GPUs are not supported")
             buf = alloc_symmetric(xbytes + fbytes, self.dev, self.e.comm.group)
+        self._pick_exchange_format(buf)
         self._xchg = {
             "buf": buf, "grid": grid, "slot_floats": slot_floats, "variant": "pairs",
             "xptrs": list(buf.ptrs), "fptrs": [p + xbytes for p in buf.ptrs],
             # NVLS multicast push (multimem.st) is opt-in: GW2V_NVLS=1 and a multicast mapping granted by the driver
-            "mc_x": buf.multicast_ptr if (buf.multicast_ptr and self._want_nvls()) else 0,
+            "mc_x": buf.multicast_ptr if (buf.multicast_ptr and self._want_nvls() and not (self.debug & 32)) else 0,
             "cta_seq": torch.zeros(nseq, dtype=torch.int32, device=self.dev),
             "err": torch.zeros(1, dtype=torch.int32, device=self.dev),
         }
         self.timing = torch.zeros(2, dtype=torch.int64, device=self.dev)
+
+    def _pick_exchange_format(self, buf):
+        """Exchange chunk format of the pair kernel (csrc/sgns_pairs.cu, PK_XSTRIDE): ``GW2V_XCHG=fast`` = 16-byte
+        {f, f, f, tag} chunks, ``safe`` = 64-bit (value, tag) words, ``auto`` (default) = fast after a start-up self-test
+        that streams 16-byte chunks between every pair of ranks and looks for torn reads (collective)."""
+        mode = os.environ.get("GW2V_XCHG", "auto")
+        if mode not in ("auto", "fast", "safe"):
+            raise ValueError(f"GW2V_XCHG must be auto, fast or safe, not {mode!r}")
+        self.xchg_selftest = None
+        if mode == "auto" and self._loopback <= 1:
+            res = torch.zeros(2, dtype=torch.int64, device=self.dev)
+            buf.local[:self.world * 32 * 16].zero_()
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.e.comm.group)
+            _C.xchg_selftest(list(buf.ptrs), self.rank, int(os.environ.get("GW2V_XCHG_SELFTEST_ITERS", "200000")), res)
+            torch.cuda.synchronize(self.dev)
+            dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.e.comm.group)
+            torn, seen = int(res[0].item()), int(res[1].item())
+            buf.local[:self.world * 32 * 16].zero_()
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.e.comm.group)
+            self.xchg_selftest = {"torn": torn, "observed": seen}
+            if torn:
+                import logging
+                logging.getLogger(__name__).warning(
+                    "exchange self-test saw %d torn 16-byte chunks in %d reads: using 64-bit tagged words", torn, seen)
+                mode = "safe"
+        if mode == "safe":
+            self.debug |= 32
 
     def _setup_tile_exchange(self):
         """Symmetric exchange ring of the tensor-core tile kernel (collective): per CTA ``slots`` x ``world`` payloads of
@@ -324,6 +354,20 @@ class CudaShardOps:
             self._step_events[self._step_i % m].record(torch.cuda.current_stream(self.dev))
             self._step_i += 1
         return stats
+
+    def prepare(self, t: int):
+        """One-time work of the first step of ``t`` tokens, callable ahead of the training loop (collective when
+        world > 1): staging buffers, hot-row tables (numpy over the whole vocabulary) and the exchange rings."""
+        self._ensure_capacity(t)
+        self._update_row_scales(t)
+        if self.world > 1 and self._xchg is None:
+            if self._tile_mode:
+                if not hasattr(self, "_tile_grid"):
+                    self._tile_neg_scale = float(self.e.tile_neg_scale())
+                    self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
+                self._setup_tile_exchange()
+            else:
+                self._setup_exchange()
 
     def _update_row_scales(self, t: int):
         """Hot-row damping tables for a step of ``t`` tokens (models/engine.py::row_scales), cached per window size."""

@@ -7,10 +7,10 @@
 set -uo pipefail
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-# TOOLS / FILTER / LIMIT can be narrowed from the environment when GPU time is short
-T="tests/test_gpu_ops.py -m gpu -q -x -k '${FILTER:-zero_pair or subsample or zipf or init_syn0 or inference}'"
+# FILES / TOOLS / FILTER / LIMIT / TAG can be narrowed from the environment when GPU time is short
+T="${FILES:-tests/test_gpu_ops.py} -m gpu -q -x -k '${FILTER:-zero_pair or subsample or zipf or init_syn0 or inference}'"
 for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   echo "== compute-sanitizer --tool $tool"
-  eval timeout ${LIMIT:-900} compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $T > gpurun_out/sanitize_$tool.log 2>&1
-  echo "exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitize_$tool.log | tail -2 | tr '\n' ' ')"
+  eval timeout ${LIMIT:-900} compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $T > gpurun_out/sanitize_${TAG:-r2}_$tool.log 2>&1
+  echo "exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitize_${TAG:-r2}_$tool.log | tail -2 | tr '\n' ' ')"
 done

@@ -336,3 +336,21 @@ def test_command_line_train_query_export(tmp_path, capsys):
     local = str(tmp_path / "local")
     assert main(["export", out, local, "--config", "device=cpu"]) == 0
     assert os.path.isdir(os.path.join(local, "data"))
+
+
+def test_parameter_server_config_reaches_the_engine_options():
+    """hot_row_cap / sampler / step_tokens of parameterServerConfig must arrive in EngineOptions (a filter list once
+    dropped hot_row_cap and sampler silently)."""
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    est = ServerSideGlintWord2Vec(inputCol="s", outputCol="v", vectorSize=8, minCount=5, seed=1, numParameterServers=1, numPartitions=3,
+                                  unigramTableSize=1000000,
+                                  parameterServerConfig={"device": "cpu", "hot_row_cap": 7.5, "sampler": "table",
+                                                         "step_tokens": 4096, "neg_sharing": "tile", "tile_negatives": 32})
+    m = est.fit(synthetic_capitals_corpus()[:300])
+    try:
+        eng = m._require_handle().engine
+        assert eng.opts.hot_row_cap == 7.5 and eng.opts.sampler == "table" and eng.opts.step_tokens == 4096
+        assert eng.opts.num_partitions == 3 and eng.opts.unigram_table_size == 1000000
+        assert eng.cfg.neg_sharing == "tile" and eng.cfg.tile_negatives == 32
+    finally:
+        m.stop()

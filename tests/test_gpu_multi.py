@@ -73,7 +73,8 @@ def _worker(rank, world, port, d, out_dir, n=5):
                 pairs.append(st.pairs)
             torch.save({"got0": got0, "ref0": ref0, "start0": start0, "pairs": pairs,
                         "stats": torch.stack(stats), "nrm": nrm, "idx": idx, "sim": sim,
-                        "avg": avg, "mul": mul, "idx16": idx16, "sim16": sim16},
+                        "avg": avg, "mul": mul, "idx16": idx16, "sim16": sim16,
+                        "xchg": eng._cuda.xchg_selftest, "debug": eng._cuda.debug},
                        os.path.join(out_dir, "result.pt"))
         dist.barrier()
     finally:
@@ -130,6 +131,26 @@ def test_fused_multi_many_negatives(world, d, n, tmp_path):
     upd_ref = r["ref0"] - r["start0"]
     upd_got = r["got0"] - r["start0"]
     assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2
+
+
+@pytest.mark.parametrize("world,d,mode", [(2, 128, "safe"), (2, 128, "auto"), (8, 512, "safe")])
+def test_pair_exchange_formats(world, d, mode, tmp_path, monkeypatch):
+    """GW2V_XCHG=safe: 64-bit (value, tag) words instead of 16-byte {f, f, f, tag} chunks (csrc/sgns_pairs.cu);
+    auto: the start-up self-test streams 16-byte chunks between all peers and must not see a torn read on this box."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("GW2V_XCHG", mode)
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), d, str(tmp_path)), nprocs=world, join=True)
+    r = torch.load(os.path.join(tmp_path, "result.pt"))
+    assert [int(x) for x in r["stats"][:, 0]] == r["pairs"]
+    upd_ref = r["ref0"] - r["start0"]
+    upd_got = r["got0"] - r["start0"]
+    assert (upd_got - upd_ref).norm() / upd_ref.norm() < 3e-2
+    if mode == "safe":
+        assert r["debug"] & 32 and r["xchg"] is None
+    else:
+        assert r["xchg"]["torn"] == 0 and r["xchg"]["observed"] > 0 and not (r["debug"] & 32)
 
 
 def _worker_tile(rank, world, port, d, nn, out_dir):

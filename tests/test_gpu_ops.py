@@ -464,9 +464,10 @@ def test_nn_select_matches_exact_topk(d, nq, k):
     cos = (qs.to(dev) / qs.to(dev).norm(dim=1, keepdim=True)) @ (wn / wn.norm(dim=1, keepdim=True).clamp(min=1e-30)).t()
     want_sim, want_idx = torch.topk(cos, k, dim=1)
     assert torch.allclose(sim, want_sim.cpu(), atol=3e-6)
-    # index sets agree except where neighbouring cosines tie within fp32 noise
-    same = [(len(set(a.tolist()) & set(b.tolist()))) for a, b in zip(idx, want_idx.cpu())]
-    assert min(same) >= k - 1 and sum(same) >= nq * k - max(2, nq // 8)
+    # the returned rows really have those cosines (rows 1000..1009 tie exactly with row 5, so index SETS may differ)
+    got_cos = torch.gather(cos.cpu(), 1, idx)
+    assert torch.allclose(got_cos, want_sim.cpu(), atol=3e-6)
+    assert all(len(set(r.tolist())) == k for r in idx)
     # training invalidates the index
     eng.set_noise(zipf_counts(v, 10 ** 7, 0.6))
     eng.train_step(np.arange(1000, dtype=np.int32), np.zeros(1000, np.int32), 0, 0, 0.025)

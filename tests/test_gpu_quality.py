@@ -40,11 +40,11 @@ def _reference():
 
 
 # Measured on a B200 (profiles/r2_quality.md; CPU reference: loss 3.382, recall@10 0.41):
-#   pair  8 192: loss 3.550 (1.050x)  recall 0.945      pair 131 072: loss 3.516 (1.040x)  recall 0.985
-#   tile  8 192: loss 3.741 (1.106x)  recall 0.895      tile 131 072: loss 3.931 (1.162x)  recall 0.42
+#   pair       8 192: loss 3.550 (1.050x)  recall 0.945      131 072: loss 3.516 (1.040x)  recall 0.985
+#   tile NN=64 8 192: loss 3.709 (1.097x)  recall 0.87       131 072: loss 3.912 (1.157x)  recall 0.435
 # The pair kernel matches the reference's mini-batches within ~5 % of the loss and finds the planted neighbours far more
 # often (many summed stale updates act like a larger step in this under-trained, single-pass regime).  Tile mode shares
-# 32 negatives among 128 centres: the same expected gradient from ~90x fewer distinct negative rows per token, i.e. a
+# 64 negatives among 128 centres: the same expected gradient from ~45x fewer distinct negative rows per token, i.e. a
 # throughput mode that needs more passes for the same loss -- its bound is wider and documented as such.
 LOSS_BOUND = {"pair": 1.06, "tile": 1.20}
 
