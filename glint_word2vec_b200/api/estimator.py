@@ -29,7 +29,7 @@ JAVA_ESTIMATOR_CLASS = "org.apache.spark.ml.feature.ServerSideGlintWord2Vec"
 
 _ENGINE_KEYS = ("step_tokens", "subsample_mode", "transport", "kernel",
                 "store_syn1", "max_hot_updates", "window_mode", "sigmoid_mode", "max_grad", "neg_sharing", "tile_centres",
-                "tile_negatives", "device", "hot_row_cap", "sampler")
+                "tile_negatives", "device", "hot_row_cap", "sampler", "tile_neg_weight")
 
 
 # keys of parameterServerConfig that configure the model spec (SGNSConfig) or the placement, not EngineOptions

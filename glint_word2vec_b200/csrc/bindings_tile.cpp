@@ -58,7 +58,7 @@ void sgns_step_tile(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Ten
                     c10::optional<Tensor> row_scale0, c10::optional<Tensor> row_scale1, c10::optional<Tensor> dbg,
                     int64_t world, int64_t rank, std::vector<int64_t> xbuf_ptrs, std::vector<int64_t> flag_ptrs,
                     c10::optional<Tensor> cta_seq, c10::optional<Tensor> error_flag, c10::optional<Tensor> timing,
-                    double tile_neg_scale) {
+                    double tile_neg_scale, double tile_neg_weight) {
     TORCH_CHECK(syn0.is_cuda() && syn1.is_cuda() && syn0.is_contiguous() && syn1.is_contiguous(), "syn0/syn1: cuda contiguous");
     TORCH_CHECK(syn0.scalar_type() == torch::kFloat32 && syn1.scalar_type() == torch::kFloat32, "syn0/syn1 must be fp32");
     TORCH_CHECK(tokens.scalar_type() == torch::kInt32 && sent_id.scalar_type() == torch::kInt32 &&
@@ -117,6 +117,7 @@ void sgns_step_tile(Tensor syn0, Tensor syn1, Tensor tokens, Tensor sent_id, Ten
         return t->data_ptr<float>();
     };
     p.tile_neg_scale = (float)tile_neg_scale;
+    p.tile_neg_weight = (float)tile_neg_weight;
     gw2v::TileLaunch l{};
     l.cinfo = reinterpret_cast<const uint32_t*>(cinfo.data_ptr<int>());
     l.tile_negs = tile_negs.data_ptr<int>();

@@ -31,6 +31,7 @@ struct SgnsParams {
     const float* row_scale1;
     int hot_rows;
     float tile_neg_scale;        // tile kernel: scale of the shared negatives' row updates (engine.tile_neg_scale)
+    float tile_neg_weight;       // tile kernel: weight of the whole negative term, both dU and dV side (1 = the reference's n)
     int compute_loss;
     int debug;                   // bit0 skip syn1 atomics, bit1 skip syn0 atomics, bit2 skip row loads (profiling);
                                  // bit3 single-GPU loopback of the exchange (profiling); bit4 random push delays (stress test)

@@ -390,7 +390,8 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             const uint32_t mask = info & 0xFFFFFFu;
             const int lo = -(int)(info >> 24);
             const int m = __popc(mask);
-            const float wneg = (float)m * nratio;
+            const float wneg = (float)m * nratio;                            // weight in the loss
+            const float wupd = wneg * p.tile_neg_weight;                     // weight in the updates (stability knob, engine.py)
             const bool has_next = tile + (int)gridDim.x < ntiles;
             if (it == 0)                                                 // the first tile's pass-A stage uses go by
                 for (int c = 0; c < NC; ++c)
@@ -415,7 +416,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 float g[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    g[j] = m > 0 ? wneg * sgns_coeff(f[j], 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
+                    g[j] = m > 0 ? wupd * sgns_coeff(f[j], 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
                     if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f[j]); maxdot = fmaxf(maxdot, fabsf(f[j])); }
                 }
                 const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;

@@ -51,6 +51,10 @@ class EngineOptions:
     # learning rate that leaves all but the most frequent rows untouched.  Applied by the fused GPU kernels (pairs and
     # tile); the un-fused path keeps the reference's exact semantics.  0 = off.
     hot_row_cap: float = 32.0
+    # neg_sharing="tile": weight of the negative term in the UPDATES, both the dU and the dV side (1 = the reference's n
+    # negatives; 0.4 behaves like n = 2).  A stability knob for constant-learning-rate runs with very large norms; the
+    # loss statistic always uses the full weight.  Scaling only one side biases the model (profiles/r2_tile_kernel.md).
+    tile_neg_weight: float = 1.0
     # asynchronous data-parallel workers of the reference (``numPartitions``, MLLIB:122-126,345,392): P workers each
     # have one mini-batch in flight against the same servers, i.e. the updates of P * batchSize centres are computed
     # from the same stale rows.  The un-fused engine path reproduces that staleness: mini-batches of
@@ -199,6 +203,10 @@ class ShardEngine:
             return 1.0
         mass = self.cfg.tile_centres * self.mean_pairs_per_centre() * self.cfg.negatives / self.cfg.tile_negatives
         return float(min(1.0, cap / max(mass, 1e-30)))
+
+    def tile_neg_weight(self) -> float:
+        """neg_sharing="tile": weight of the negative term in the updates (both sides; 1 = the reference's n)."""
+        return float(self.opts.tile_neg_weight)
 
     def row_scales(self, window_tokens: int):
         """Hot-row damping tables ``(scale0, scale1)`` (float32, length = number of hot rows H; rows >= H are 1).

@@ -99,7 +99,7 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
         words_it = 0
         skip = start_step if k == start_iteration else 0
         # steps are cut (memory-mapped token slices, sentence ids) by a background thread, PREFETCH steps ahead
-        for si, batch in enumerate(_prefetch(iter_steps(corpus, step_tokens), PREFETCH)):
+        for si, batch in enumerate(_prefetch(_pinned(iter_steps(corpus, step_tokens), engine, step_tokens), PREFETCH)):
             if si < skip:
                 words_it += batch.n_words
                 continue
@@ -109,7 +109,9 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
             pending.append(stats)
             words_it += batch.n_words
             rep.steps += 1
-            if (words_prev + words_it - last_log > log_every_words and len(pending) > lag) or len(pending) >= 64:
+            # GPU: a metrics record every >= 8 steps (a record per 131 072-token step costs more host time than the step)
+            if (words_prev + words_it - last_log > max(log_every_words, lag * 4 * step_tokens) and len(pending) > lag) \
+                    or len(pending) >= 64:
                 last_log = words_prev + words_it
                 ready = pending[:len(pending) - lag]
                 del pending[:len(pending) - lag]
@@ -130,6 +132,33 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
 
 
 PREFETCH = 4
+
+
+def _pinned(steps, engine, step_tokens: int):
+    """GPU engines: copy every step's arrays into pinned host buffers INSIDE the producer thread, so the launch loop
+    hands pinned tensors to ``stage_tokens`` (asynchronous H2D straight from them, no host memcpy on the main thread).
+    The pool is a ring of PREFETCH + staging slots + 2 buffers: the host can be at most that many steps ahead of the
+    copy engine (``stage_tokens`` blocks on the slot's free event), so a buffer is never rewritten before its H2D ran."""
+    if not engine.is_cuda or engine.unfused:
+        yield from steps
+        return
+    from ..data.corpus import StepBatch
+    from ..ops.cuda import N_STAGE
+    n = PREFETCH + N_STAGE + 2
+    cap = max(1, int(step_tokens))
+    pool = [(torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
+            for _ in range(n)]
+    i = 0
+    for b in steps:
+        t = int(b.tokens.shape[0])
+        if t > cap:                                   # cannot happen with iter_steps; keep the slow path correct
+            yield b
+            continue
+        pt, ps = pool[i]
+        i = (i + 1) % n
+        pt[:t].copy_(torch.from_numpy(np.ascontiguousarray(b.tokens, dtype=np.int32)))
+        ps[:t].copy_(torch.from_numpy(np.ascontiguousarray(b.sent_id, dtype=np.int32)))
+        yield StepBatch(pt[:t], ps[:t], b.raw_pos0, b.n_words)
 
 
 def _prefetch(it, depth: int):

@@ -104,6 +104,7 @@ class CudaShardOps:
         self.row_scale0: Optional[torch.Tensor] = None     # per-row update scales of the first H rows (hot-row damping)
         self.row_scale1: Optional[torch.Tensor] = None
         self._scale_window = -1
+        self._scale_cache = {}
         self.tile_dbg: Optional[torch.Tensor] = None       # tests: dot products of tile 0
         # sigmoid_mode="table": the reference's 1000-entry sigma table (MLLIB:281-302), looked up in-kernel
         self.exp_table = None
@@ -135,6 +136,7 @@ class CudaShardOps:
 
     def upload_noise(self, alias, keep_thresh: np.ndarray):
         self._scale_window = -1               # the damping tables depend on the counts
+        self._scale_cache = {}
         self.alias_dev = torch.from_numpy(alias.packed()).to(self.dev)
         self.keep_dev = torch.from_numpy(keep_thresh.view(np.int32).copy()).to(self.dev)
         self.subsample_active = bool((keep_thresh != U32_MAX).any())
@@ -363,7 +365,8 @@ class CudaShardOps:
         if self.world > 1 and self._xchg is None:
             if self._tile_mode:
                 if not hasattr(self, "_tile_grid"):
-                    self._tile_neg_scale = float(self.e.tile_neg_scale())
+                    self._tile_neg_scale = float(os.environ.get("GW2V_TILE_NEG_SCALE", self.e.tile_neg_scale()))
+                    self._tile_neg_weight = float(os.environ.get("GW2V_TILE_NEG_WEIGHT", self.e.tile_neg_weight()))
                     self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
                 self._setup_tile_exchange()
             else:
@@ -374,13 +377,19 @@ class CudaShardOps:
         w = self.e.inflight_tokens(t)
         if w == self._scale_window:
             return
+        # a short tail step has a smaller window; the tables are cached per (power-of-two) window so that alternating
+        # between full and tail steps does not redo the numpy pass over the vocabulary (0.3 s at V = 10 M)
+        w = 1 << max(0, int(w - 1).bit_length())
+        if w == self._scale_window:
+            return
         self._scale_window = w
-        sc = self.e.row_scales(w)
-        if sc is None or sc[0].shape[0] == 0:
-            self.row_scale0 = self.row_scale1 = None
-        else:
-            self.row_scale0 = torch.from_numpy(sc[0]).to(self.dev)
-            self.row_scale1 = torch.from_numpy(sc[1]).to(self.dev)
+        if w not in self._scale_cache:
+            sc = self.e.row_scales(w)
+            if sc is None or sc[0].shape[0] == 0:
+                self._scale_cache[w] = (None, None)
+            else:
+                self._scale_cache[w] = (torch.from_numpy(sc[0]).to(self.dev), torch.from_numpy(sc[1]).to(self.dev))
+        self.row_scale0, self.row_scale1 = self._scale_cache[w]
 
     def _train_step_device_impl(self, tok_dev, sid_dev, t, raw_pos0, iteration, alpha) -> torch.Tensor:
         cfg = self.cfg
@@ -405,7 +414,8 @@ class CudaShardOps:
         wm = WINDOW_MODES[cfg.window_mode]
         if self._tile_mode:
             if not hasattr(self, "_tile_grid"):
-                self._tile_neg_scale = float(e.tile_neg_scale())
+                self._tile_neg_scale = float(os.environ.get("GW2V_TILE_NEG_SCALE", e.tile_neg_scale()))
+                self._tile_neg_weight = float(os.environ.get("GW2V_TILE_NEG_WEIGHT", e.tile_neg_weight()))
                 self._tile_grid = int(os.environ.get("GW2V_TILE_GRID", self._props.multi_processor_count))
             if self.world > 1 and self._xchg is None:
                 self._setup_tile_exchange()
@@ -417,7 +427,7 @@ class CudaShardOps:
                               self.exp_table, self.row_scale0, self.row_scale1, self.tile_dbg,
                               self.world, self.rank, x["xptrs"] if x else [], x["fptrs"] if x else [],
                               x["cta_seq"] if x else None, x["err"] if x else None, self.timing if x else None,
-                              self._tile_neg_scale)
+                              self._tile_neg_scale, self._tile_neg_weight)
             self.launches += 4            # pair_count, pair_tile_scan, tile_negs, sgns_tile
             return stats
         # pair_count, pair_tile_scan (zeroes the statistics), pair_fill, then the training kernel
