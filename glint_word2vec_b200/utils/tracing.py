@@ -38,11 +38,13 @@ class StepTimer:
         self.totals_ms: Dict[str, float] = defaultdict(float)
         self.counts: Dict[str, int] = defaultdict(int)
         self._pending = []
+        self._pool = []             # recycled CUDA events (creating one costs ~0.4 ms)
 
     @contextlib.contextmanager
     def region(self, label: str):
         if self.cuda:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0 = self._pool.pop() if self._pool else torch.cuda.Event(enable_timing=True)
+            e1 = self._pool.pop() if self._pool else torch.cuda.Event(enable_timing=True)
             e0.record()
             with nvtx_range(label):
                 yield
@@ -61,6 +63,7 @@ class StepTimer:
                 label, e0, e1 = self._pending.pop(0)
                 self.totals_ms[label] += e0.elapsed_time(e1)
                 self.counts[label] += 1
+                self._pool += [e0, e1]
         return {k: {"ms": v, "n": self.counts[k]} for k, v in self.totals_ms.items()}
 
     def flush(self):
@@ -69,5 +72,6 @@ class StepTimer:
             for label, e0, e1 in self._pending:
                 self.totals_ms[label] += e0.elapsed_time(e1)
                 self.counts[label] += 1
+                self._pool += [e0, e1]
             self._pending.clear()
         return {k: {"ms": v, "n": self.counts[k]} for k, v in self.totals_ms.items()}

@@ -441,3 +441,51 @@ def test_checkpoint_pruning_never_deletes_latest_and_stale_runs_are_refused(tmp_
     with pytest.raises(ValueError, match="does not belong to this run"):
         checkpoint.resume(d, other, np.arange(v, 0, -1), Comm(), torch.device("cpu"),
                           EngineOptions(subsample_mode="reference", hot_row_cap=0))
+
+
+def test_step_prefetch_keeps_order_and_propagates_errors():
+    """models/trainer.py::_prefetch: the background producer hands items over in order, re-raises its exception in
+    the consumer, and stops when the consumer walks away."""
+    from glint_word2vec_b200.models.trainer import _prefetch
+    assert list(_prefetch(iter(range(100)), 4)) == list(range(100))
+
+    def boom():
+        yield 1
+        yield 2
+        raise RuntimeError("producer failed")
+    got = []
+    with pytest.raises(RuntimeError, match="producer failed"):
+        for x in _prefetch(boom(), 2):
+            got.append(x)
+    assert got == [1, 2]
+    produced = []
+
+    def slow():
+        for i in range(1000):
+            produced.append(i)
+            yield i
+    g = _prefetch(slow(), 2)
+    assert next(g) == 0
+    g.close()                                  # abandoned consumer: the producer must stop within its hand-over timeout
+    import time
+    time.sleep(0.6)
+    n = len(produced)
+    time.sleep(0.4)
+    assert len(produced) == n and n < 20
+
+
+def test_training_report_carries_phase_times(tmp_path):
+    """StepTimer is wired into trainer.train: cumulative per-phase times in every metrics record and in the report."""
+    import json
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    from glint_word2vec_b200 import ServerSideGlintWord2Vec
+    mp = tmp_path / "metrics.jsonl"
+    m = ServerSideGlintWord2Vec(inputCol="s", outputCol="v", vectorSize=8, minCount=5, seed=1, numParameterServers=1,
+                                parameterServerConfig={"device": "cpu", "metrics_path": str(mp)}).fit(synthetic_capitals_corpus()[:400])
+    try:
+        rep = m.trainingReport
+        assert rep["device_ms"]["sgns_step"]["n"] == rep["steps"] and rep["device_ms"]["sgns_step"]["ms"] > 0
+        recs = [json.loads(l) for l in mp.read_text().splitlines()]
+        assert recs and "device_ms" in recs[-1] and "pairs_per_sec" in recs[-1]
+    finally:
+        m.stop()
