@@ -330,7 +330,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                     v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
                     for (int r = 0; r < p.world; ++r) {
                         const int src = loop ? r : p.rank;
-                        float* dst = p.xbuf[r] + ((slot_base + src) * TL_T + (size_t)row) * PAYF + f0;
+                        // payload layout [float4 index][centre][4]: the 32 lanes of a warp store 512 contiguous bytes
+                        // (one coalesced NVLink write instead of 32 scattered 16-byte ones -- the row-major layout made
+                        // the push of an 8-shard run 7x slower than the compute of the tile, profiles/r2_scale.md)
+                        float* dst = p.xbuf[r] + (slot_base + src) * TL_T * PAYF + ((size_t)(f0 >> 2) * TL_T + (size_t)row) * 4;
                         asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                                      ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                     }
@@ -485,7 +488,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                     if (p.timing != nullptr) atomicAdd(p.timing, tc_globaltimer_ns() - t0);
                 }
                 epi_bar();
-                const float* xin = p.xbuf[p.rank] + (slot_base * TL_T + (size_t)row) * PAYF;      // + src * 128 * PAYF
+                const float* xin = p.xbuf[p.rank] + slot_base * TL_T * PAYF + (size_t)row * 4;    // + src * 128 * PAYF + j * 128 * 4
                 auto ld_sys = [](const float* ptr) {
                     float4 v;
                     asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -501,7 +504,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         if ((s4 < S4H) != (grp == 0)) continue;
                         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int src = 0; src < p.world; ++src) {
-                            const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + 4 * s4);
+                            const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + (size_t)s4 * TL_T * 4);
                             t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
                         }
                         band_emit(4 * s4 + 0 - WM, t.x); band_emit(4 * s4 + 1 - WM, t.y);
@@ -517,7 +520,7 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                         for (int src = 0; src < p.world; ++src) {
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + SLP + 16 * h + 4 * j4);
+                                const float4 v = ld_sys(xin + (size_t)src * TL_T * PAYF + (size_t)(SLP / 4 + 4 * h + j4) * TL_T * 4);
                                 f[4 * j4] += v.x; f[4 * j4 + 1] += v.y; f[4 * j4 + 2] += v.z; f[4 * j4 + 3] += v.w;
                             }
                         }

@@ -373,7 +373,8 @@ class ShardEngine:
         fplus, fminus = full[:ci.shape[0]], full[ci.shape[0]:].view(len(centres), nn)
         wgt = torch.from_numpy(m.astype(np.float64) * cfg.negatives / nn).to(torch.float32).to(dev)
         gplus = sgns.sigmoid_coeff(fplus, 1.0, alpha, cfg.sigmoid_mode, cfg.max_grad)
-        gminus = sgns.sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * wgt[:, None]
+        # tile_neg_weight scales the negative term of the UPDATES (both sides); the loss keeps the full weight
+        gminus = sgns.sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * (wgt * float(self.opts.tile_neg_weight))[:, None]
         stats.loss = float(sgns.sgns_loss(fplus, fminus, wgt[:, None].expand_as(fminus)))
         stats.max_abs_dot = float(full.abs().max())
         du_neg = torch.empty_like(ua)
