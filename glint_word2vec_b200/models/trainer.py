@@ -148,6 +148,7 @@ def _pinned(steps, engine, step_tokens: int):
     cap = max(1, int(step_tokens))
     pool = [(torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
             for _ in range(n)]
+    views = [(a.numpy(), b.numpy()) for a, b in pool]       # numpy views: plain memcpy, works for read-only memory maps
     i = 0
     for b in steps:
         t = int(b.tokens.shape[0])
@@ -155,9 +156,10 @@ def _pinned(steps, engine, step_tokens: int):
             yield b
             continue
         pt, ps = pool[i]
+        vt, vs = views[i]
         i = (i + 1) % n
-        pt[:t].copy_(torch.from_numpy(np.ascontiguousarray(b.tokens, dtype=np.int32)))
-        ps[:t].copy_(torch.from_numpy(np.ascontiguousarray(b.sent_id, dtype=np.int32)))
+        vt[:t] = b.tokens
+        vs[:t] = b.sent_id
         yield StepBatch(pt[:t], ps[:t], b.raw_pos0, b.n_words)
 
 

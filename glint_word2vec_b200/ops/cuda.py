@@ -38,6 +38,9 @@ class _StageSlot:
     def __init__(self, cap: int, dev):
         self.pin_tok = torch.empty(cap, dtype=torch.int32).pin_memory()
         self.pin_sid = torch.empty(cap, dtype=torch.int32).pin_memory()
+        # numpy views of the pinned buffers: a host-side torch copy_ of 0.5 MB enters an OpenMP region and was measured
+        # at ~2 ms on a many-core box (4.7 of the 6 ms per step of the fit loop); a plain numpy memcpy is ~50 us
+        self.pin_tok_np, self.pin_sid_np = self.pin_tok.numpy(), self.pin_sid.numpy()
         self.tok = torch.empty(cap, dtype=torch.int32, device=dev)
         self.sid = torch.empty(cap, dtype=torch.int32, device=dev)
         self.h2d_ev = torch.cuda.Event()
@@ -302,8 +305,8 @@ class CudaShardOps:
                 and sent_id.is_pinned():
             src_tok, src_sid = tokens, sent_id
         else:
-            slot.pin_tok[:t].copy_(torch.as_tensor(np.ascontiguousarray(tokens, dtype=np.int32)))
-            slot.pin_sid[:t].copy_(torch.as_tensor(np.ascontiguousarray(sent_id, dtype=np.int32)))
+            slot.pin_tok_np[:t] = tokens.numpy() if isinstance(tokens, torch.Tensor) else tokens
+            slot.pin_sid_np[:t] = sent_id.numpy() if isinstance(sent_id, torch.Tensor) else sent_id
             src_tok, src_sid = slot.pin_tok[:t], slot.pin_sid[:t]
         cs = self._copy_stream
         with torch.cuda.stream(cs):

@@ -53,6 +53,11 @@ def main():
     out["vocab_kept"] = model.numWords
     out["encoded_bytes"] = 4 * rep["words"]
     out["peak_rss_mb"] = round(rss_mb())
+    # ru_maxrss counts file-backed pages of the memory-mapped text and token files too; the anonymous part is what the
+    # process really holds
+    for line in open("/proc/self/status"):
+        if line.startswith(("RssAnon", "RssFile", "VmHWM")):
+            out[line.split(":")[0].lower() + "_mb"] = round(int(line.split()[1]) / 1024)
     model.stop()
     print(json.dumps(out), flush=True)
     import shutil
