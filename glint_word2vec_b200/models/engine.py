@@ -184,8 +184,12 @@ class ShardEngine:
         if not self.is_cuda or self.unfused:
             return max(1, self.opts.batch_size) * max(1, self.opts.num_partitions)
         if self.cfg.neg_sharing == "tile":
-            return min(int(step_tokens), 148 * self.cfg.tile_centres)      # one tile per SM in flight
-        return min(int(step_tokens), 4096)                                  # resident warps x pairs of the pair kernel
+            w = min(int(step_tokens), 148 * self.cfg.tile_centres)         # one tile per SM in flight
+        else:
+            w = min(int(step_tokens), 4096)                                 # resident warps x pairs of the pair kernel
+        # rounded up to a power of two: short tail steps then share the damping tables of a handful of window sizes
+        # instead of each paying a numpy pass over the vocabulary (ops/cuda.py::_update_row_scales caches per window)
+        return 1 << max(0, int(max(1, w) - 1).bit_length())
 
     def mean_pairs_per_centre(self) -> float:
         w = self.cfg.window

@@ -137,14 +137,16 @@ PREFETCH = 4
 def _pinned(steps, engine, step_tokens: int):
     """GPU engines: copy every step's arrays into pinned host buffers INSIDE the producer thread, so the launch loop
     hands pinned tensors to ``stage_tokens`` (asynchronous H2D straight from them, no host memcpy on the main thread).
-    The pool is a ring of PREFETCH + staging slots + 2 buffers: the host can be at most that many steps ahead of the
+    The pool is a ring of PREFETCH + 2 x staging slots + 4 buffers: the host can be at most that many steps ahead of the
     copy engine (``stage_tokens`` blocks on the slot's free event), so a buffer is never rewritten before its H2D ran."""
     if not engine.is_cuda or engine.unfused:
         yield from steps
         return
     from ..data.corpus import StepBatch
     from ..ops.cuda import N_STAGE
-    n = PREFETCH + N_STAGE + 2
+    # in flight at once: N_STAGE steps whose H2D may still be pending + the one being launched + PREFETCH queued + one
+    # being written by this thread, and the launch loop learns about completions one step late -> 2 * N_STAGE of margin
+    n = PREFETCH + 2 * N_STAGE + 4
     cap = max(1, int(step_tokens))
     pool = [(torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
             for _ in range(n)]

@@ -380,11 +380,8 @@ class CudaShardOps:
         w = self.e.inflight_tokens(t)
         if w == self._scale_window:
             return
-        # a short tail step has a smaller window; the tables are cached per (power-of-two) window so that alternating
+        # a short tail step has a smaller (power-of-two) window; the tables are cached per window so that alternating
         # between full and tail steps does not redo the numpy pass over the vocabulary (0.3 s at V = 10 M)
-        w = 1 << max(0, int(w - 1).bit_length())
-        if w == self._scale_window:
-            return
         self._scale_window = w
         if w not in self._scale_cache:
             sc = self.e.row_scales(w)
