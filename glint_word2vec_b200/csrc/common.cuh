@@ -90,6 +90,33 @@ __device__ __forceinline__ float sgns_coeff(float f, float label, float alpha, f
     return g;
 }
 
+// coefficient and loss term of one dot product from ONE exponential (tile kernel epilogue: ~70 of these per thread and
+// tile).  label 1: loss = log(1 + e^-f);  label 0: loss = log(1 + e^f) = f + log(1 + e^-f);  f clipped to +-MAX_EXP in
+// the loss exactly like softplus_clipped; the reciprocal is the approximate one (2 ulp).
+__device__ __forceinline__ float sgns_coeff_loss(float f, float label, float alpha, float max_grad,
+                                                 const float* __restrict__ table, bool want_loss, float& loss) {
+    const float fc = fminf(fmaxf(f, -MAX_EXP), MAX_EXP);
+    const float e = __expf(-fc);
+    float sig;
+    if (table != nullptr) {
+        int ind = (int)((f + MAX_EXP) * 83.0f);
+        ind = min(max(ind, 0), 999);
+        sig = __ldg(table + ind);
+    } else {
+        sig = __fdividef(1.0f, 1.0f + e);
+    }
+    float g = label - sig;
+    if (f > MAX_EXP) g = label - 1.0f;
+    if (f < -MAX_EXP) g = label;
+    g *= alpha;
+    if (max_grad > 0.0f) g = fminf(fmaxf(g, -max_grad), max_grad);
+    if (want_loss) {
+        const float l1 = __logf(1.0f + e);
+        loss = label > 0.5f ? l1 : l1 + fc;
+    }
+    return g;
+}
+
 // per-row update scale of the hot-row damping (1 beyond the first `hot_rows` rows)
 __device__ __forceinline__ float row_scale(const float* __restrict__ tab, int hot_rows, int row) {
     return (tab != nullptr && row < hot_rows) ? __ldg(tab + row) : 1.0f;

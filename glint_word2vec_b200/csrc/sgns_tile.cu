@@ -404,14 +404,15 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             if (etid < TL_CTX) *reinterpret_cast<uint32_t*>(sm + C::MASK_OFF + etid * 4) = 0u;
             epi_bar();
             // one (centre, context) candidate: coefficient into bandT / maskT
-            auto band_emit = [&](int off, float f) {
+            auto band_emit = [&](int off, float f, bool known_valid = false) {
                 const int bit = off - lo;
-                if (bit >= 0 && bit < 24 && ((mask >> bit) & 1u)) {
-                    const float g = sgns_coeff(f, 1.f, p.alpha, p.max_grad, p.exp_table);
+                if (known_valid || (bit >= 0 && bit < 24 && ((mask >> bit) & 1u))) {
+                    float l = 0.f;
+                    const float g = sgns_coeff_loss(f, 1.f, p.alpha, p.max_grad, p.exp_table, p.compute_loss != 0, l);
                     const int cr = row + TL_HALO + off;                  // context row of the pair, slot = win - off
                     sts1(sm, C::BAND_OFF + (uint32_t)(cr * TL_GB_STRIDE + win - off) * 4, g);
                     atomicOr(reinterpret_cast<unsigned int*>(sm + C::MASK_OFF + cr * 4), 1u << (win - off));
-                    if (p.compute_loss) { loss += softplus_clipped(-f); maxdot = fmaxf(maxdot, fabsf(f)); }
+                    if (p.compute_loss) { loss += l; maxdot = fmaxf(maxdot, fabsf(f)); }
                 }
             };
             // 16 (centre, shared negative) dots: coefficients into Gneg in both operand layouts
@@ -419,8 +420,10 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 float g[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    g[j] = m > 0 ? wupd * sgns_coeff(f[j], 0.f, p.alpha, p.max_grad, p.exp_table) : 0.f;
-                    if (m > 0 && p.compute_loss) { loss += wneg * softplus_clipped(f[j]); maxdot = fmaxf(maxdot, fabsf(f[j])); }
+                    float l = 0.f;
+                    const float c = sgns_coeff_loss(f[j], 0.f, p.alpha, p.max_grad, p.exp_table, p.compute_loss != 0, l);
+                    g[j] = m > 0 ? wupd * c : 0.f;
+                    if (m > 0 && p.compute_loss) { loss += wneg * l; maxdot = fmaxf(maxdot, fabsf(f[j])); }
                 }
                 const uint32_t rowoff = (uint32_t)(h >> 1) * TL_BLOCK_BYTES + (uint32_t)row * 128;
 #pragma unroll
@@ -440,13 +443,17 @@ sgns_tile_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 {
                     // band of the context block: columns [32q, 32q + 64) of S hold every context of centres 32q..32q+31
 #pragma unroll 1
+                    // window-column mask of this centre: bit c set <=> column c of [32q, 32q + 64) is one of its contexts
+                    // (mask bit b <-> offset lo + b <-> column 16 + lane + lo + b; lo >= -11, so the shift is >= 5)
+                    const unsigned long long colmask = (unsigned long long)mask << (TL_HALO + lane + lo);
                     for (int h = 2 * grp; h < 2 * grp + 2; ++h) {
                         uint32_t x[16];
                         tmem_ld16(lane_addr + (uint32_t)(32 * q + 16 * h), x);
                         tmem_ld_wait();
+                        const uint32_t cm = (uint32_t)(colmask >> (16 * h)) & 0xFFFFu;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            band_emit(16 * h + j - TL_HALO - lane, __uint_as_float(x[j]));
+                            if ((cm >> j) & 1u) band_emit(16 * h + j - TL_HALO - lane, __uint_as_float(x[j]), true);
                             if (a.dbg != nullptr && tile == 0) a.dbg[(size_t)row * R + 32 * q + 16 * h + j] = __uint_as_float(x[j]);
                         }
                     }
