@@ -37,3 +37,12 @@ try:
     _hyp_settings.load_profile("ci")
 except ImportError:                                   # hypothesis is optional
     pass
+
+
+# denormal arithmetic is 50-100x slower on x86 and whether a torch worker thread flushes them depends on which thread
+# loaded which library first; the CPU suite must not depend on that
+try:
+    import torch as _torch
+    _torch.set_flush_denormal(True)
+except Exception:  # pragma: no cover
+    pass
