@@ -49,6 +49,8 @@ def build_parser() -> argparse.ArgumentParser:
     tr.add_argument("--subsample-ratio", type=float, default=1e-6)
     tr.add_argument("--num-servers", type=int, default=1, help="column shards = GPUs (numParameterServers)")
     tr.add_argument("--server-host", default="", help="attach to a separate shard-server group ip[:port]")
+    tr.add_argument("--num-partitions", type=int, default=1, help="asynchronous workers of the reference (staleness window)")
+    tr.add_argument("--unigram-table-size", type=int, default=100_000_000, help="with --config sampler=table")
     tr.add_argument("--seed", type=int, default=None)
     tr.add_argument("--config", action="append", metavar="KEY=VALUE",
                     help="engine option (parameterServerConfig), e.g. subsample_mode=word2vec, device=cpu")
@@ -83,13 +85,17 @@ def main(argv: Optional[List[str]] = None) -> int:
             stepSize=args.step_size, maxIter=args.max_iter, minCount=args.min_count,
             maxSentenceLength=args.max_sentence_length, batchSize=args.batch_size, n=args.n,
             subsampleRatio=args.subsample_ratio, numParameterServers=args.num_servers,
+            numPartitions=args.num_partitions, unigramTableSize=args.unigram_table_size,
             parameterServerHost=args.server_host, parameterServerConfig=_kv(args.config))
         if args.seed is not None:
             est.setSeed(args.seed)
         model = est.fitTextFile(args.corpus, args.tokenizer)
         try:
             model.save(args.out)
-            print(json.dumps({"words": model.numWords, "vector_size": model.getVectorSize(), "model": args.out}))
+            rep = model.trainingReport or {}
+            print(json.dumps({"words": model.numWords, "vector_size": model.getVectorSize(), "model": args.out,
+                              "pairs": rep.get("pairs"), "seconds": rep.get("seconds"),
+                              "loss_per_pair": rep.get("loss_per_pair")}))
         finally:
             model.stop()
         return 0
