@@ -82,8 +82,14 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
     train_words = n_tok if train_words is None else train_words
     total_words = num_iterations * train_words
     step_tokens = auto_step_tokens(engine, n_tok)
+    pool = None
     if engine.is_cuda and not engine.unfused:
-        engine._cuda.prepare(min(step_tokens, max(1, n_tok)))      # buffers, damping tables, exchange rings: not per-step work
+        # one-time work outside the clock: buffers, damping tables, exchange rings, the pinned producer pool, and a
+        # zero-token step that makes the driver load every kernel of the step (lazy module loading: ~0.2 s)
+        engine._cuda.prepare(min(step_tokens, max(1, n_tok)))
+        pool = _PinnedPool(step_tokens)
+        if engine.comm.world == 1:                  # (column shards: the first real step does it; not validated on > 1 GPU)
+            engine._cuda.warmup()
         torch.cuda.synchronize(engine.device)
     t0 = time.time()
     pending = []
@@ -99,7 +105,7 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
         words_it = 0
         skip = start_step if k == start_iteration else 0
         # steps are cut (memory-mapped token slices, sentence ids) by a background thread, PREFETCH steps ahead
-        for si, batch in enumerate(_prefetch(_pinned(iter_steps(corpus, step_tokens), engine, step_tokens), PREFETCH)):
+        for si, batch in enumerate(_prefetch(_pinned(iter_steps(corpus, step_tokens), pool), PREFETCH)):
             if si < skip:
                 words_it += batch.n_words
                 continue
@@ -134,32 +140,37 @@ def train(engine: ShardEngine, corpus: EncodedCorpus, learning_rate: float, num_
 PREFETCH = 4
 
 
-def _pinned(steps, engine, step_tokens: int):
+class _PinnedPool:
+    """Ring of pinned host buffers shared by all passes of one ``train`` call (allocated before the clock starts:
+    32 ``cudaHostAlloc`` calls cost ~0.15 s).  PREFETCH + 2 x staging slots + 4 buffers: the host can be at most that many
+    steps ahead of the copy engine (``stage_tokens`` blocks on the slot's free event; the launch loop learns about
+    completions one step late), so a buffer is never rewritten before its H2D ran."""
+
+    def __init__(self, step_tokens: int):
+        from ..ops.cuda import N_STAGE
+        self.n = PREFETCH + 2 * N_STAGE + 4
+        self.cap = max(1, int(step_tokens))
+        self.bufs = [(torch.empty(self.cap, dtype=torch.int32).pin_memory(), torch.empty(self.cap, dtype=torch.int32).pin_memory())
+                     for _ in range(self.n)]
+        self.views = [(a.numpy(), b.numpy()) for a, b in self.bufs]      # numpy views: plain memcpy, read-only maps are fine
+        self.i = 0
+
+
+def _pinned(steps, pool: Optional["_PinnedPool"]):
     """GPU engines: copy every step's arrays into pinned host buffers INSIDE the producer thread, so the launch loop
-    hands pinned tensors to ``stage_tokens`` (asynchronous H2D straight from them, no host memcpy on the main thread).
-    The pool is a ring of PREFETCH + 2 x staging slots + 4 buffers: the host can be at most that many steps ahead of the
-    copy engine (``stage_tokens`` blocks on the slot's free event), so a buffer is never rewritten before its H2D ran."""
-    if not engine.is_cuda or engine.unfused:
+    hands pinned tensors to ``stage_tokens`` (asynchronous H2D straight from them, no host memcpy on the main thread)."""
+    if pool is None:
         yield from steps
         return
     from ..data.corpus import StepBatch
-    from ..ops.cuda import N_STAGE
-    # in flight at once: N_STAGE steps whose H2D may still be pending + the one being launched + PREFETCH queued + one
-    # being written by this thread, and the launch loop learns about completions one step late -> 2 * N_STAGE of margin
-    n = PREFETCH + 2 * N_STAGE + 4
-    cap = max(1, int(step_tokens))
-    pool = [(torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
-            for _ in range(n)]
-    views = [(a.numpy(), b.numpy()) for a, b in pool]       # numpy views: plain memcpy, works for read-only memory maps
-    i = 0
     for b in steps:
         t = int(b.tokens.shape[0])
-        if t > cap:                                   # cannot happen with iter_steps; keep the slow path correct
+        if t > pool.cap:                              # cannot happen with iter_steps; keep the slow path correct
             yield b
             continue
-        pt, ps = pool[i]
-        vt, vs = views[i]
-        i = (i + 1) % n
+        pt, ps = pool.bufs[pool.i]
+        vt, vs = pool.views[pool.i]
+        pool.i = (pool.i + 1) % pool.n
         vt[:t] = b.tokens
         vs[:t] = b.sent_id
         yield StepBatch(pt[:t], ps[:t], b.raw_pos0, b.n_words)

@@ -365,6 +365,7 @@ class CudaShardOps:
         world > 1): staging buffers, hot-row tables (numpy over the whole vocabulary) and the exchange rings."""
         self._ensure_capacity(t)
         self._update_row_scales(t)
+        self._prepared_t = int(t)
         if self.world > 1 and self._xchg is None:
             if self._tile_mode:
                 if not hasattr(self, "_tile_grid"):
@@ -374,6 +375,12 @@ class CudaShardOps:
                 self._setup_tile_exchange()
             else:
                 self._setup_exchange()
+
+    def warmup(self):
+        """Launch one step over a single token with alpha = 0: every kernel of the step runs (and is loaded by the driver)
+        without touching the weights (one token has no context, a zero-pair step is a no-op); collective like any step."""
+        z = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._train_step_device_impl(z, z, 1, 0, 0, 0.0, scale_t=getattr(self, "_prepared_t", 1))
 
     def _update_row_scales(self, t: int):
         """Hot-row damping tables for a step of ``t`` tokens (models/engine.py::row_scales), cached per window size."""
@@ -391,11 +398,11 @@ class CudaShardOps:
                 self._scale_cache[w] = (torch.from_numpy(sc[0]).to(self.dev), torch.from_numpy(sc[1]).to(self.dev))
         self.row_scale0, self.row_scale1 = self._scale_cache[w]
 
-    def _train_step_device_impl(self, tok_dev, sid_dev, t, raw_pos0, iteration, alpha) -> torch.Tensor:
+    def _train_step_device_impl(self, tok_dev, sid_dev, t, raw_pos0, iteration, alpha, scale_t=None) -> torch.Tensor:
         cfg = self.cfg
         e = self.e
         self._ensure_capacity(t)
-        self._update_row_scales(t)
+        self._update_row_scales(t if scale_t is None else scale_t)
         if self.world > 1 and self._xchg is None and not self._tile_mode:
             self._setup_exchange()
         if self.subsample_active:

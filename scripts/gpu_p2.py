@@ -31,10 +31,10 @@ def loop(name, steps_iter, use_async=True, n=None):
     print(f"{name:55s} {k} steps  {dt / k * 1e3:.3f} ms/step", flush=True)
 for rep in range(2):
     loop("plain iter_steps (numpy -> stage copies)", iter_steps(corpus, B))
-    loop("iter_steps + _pinned (main thread)", T._pinned(iter_steps(corpus, B), eng, B))
+    loop("iter_steps + _pinned (main thread)", T._pinned(iter_steps(corpus, B), T._PinnedPool(B)))
     loop("_prefetch(iter_steps)", T._prefetch(iter_steps(corpus, B), 4))
-    loop("_prefetch(_pinned(iter_steps))  [trainer]", T._prefetch(T._pinned(iter_steps(corpus, B), eng, B), 4))
-    b0 = next(iter(T._pinned(iter_steps(corpus, B), eng, B)))
+    loop("_prefetch(_pinned(iter_steps))  [trainer]", T._prefetch(T._pinned(iter_steps(corpus, B), T._PinnedPool(B)), 4))
+    b0 = next(iter(T._pinned(iter_steps(corpus, B), T._PinnedPool(B))))
     print("pinned?", b0.tokens.is_pinned(), b0.sent_id.is_pinned(), type(b0.tokens))
     class One:
         def __iter__(self): return (b0 for _ in range(60))
