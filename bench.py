@@ -133,6 +133,8 @@ def main():
         os.write(real_stdout, (line + "\n").encode())
 
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:       # launched through torchrun: one line for the whole job
+            return 0
         emit(json.dumps({"impl": "reference",
                          "unavailable": "reference is a Scala/sbt Spark+Glint project (no setup.py/pyproject, needs "
                                          "JVM+sbt+network fetch of the Glint fork; contains no GPU code) - pip "
