@@ -229,7 +229,8 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
                              pos0: int, iteration: int, alpha: float,
                              lo: int = 0, hi: Optional[int] = None,
                              row_scale0: Optional[torch.Tensor] = None,
-                             row_scale1: Optional[torch.Tensor] = None, tile_neg_scale: float = 1.0) -> StepStats:
+                             row_scale1: Optional[torch.Tensor] = None, tile_neg_scale: float = 1.0,
+                             tile_neg_weight: float = 1.0) -> StepStats:
     """One mini-batch (centres ``lo..hi`` of the step) applied in place.
 
     All dots use pre-update rows; all updates are summed (index_add), i.e. the
@@ -243,7 +244,7 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
         return stats                      # zero-pair batches are a clean no-op (Q4)
     if cfg.neg_sharing == "tile":
         return _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
-                                         row_scale0, row_scale1, tile_neg_scale)
+                                         row_scale0, row_scale1, tile_neg_scale, tile_neg_weight)
     pos = np.uint64(pos0) + ci.astype(np.uint64)
     neg = draw_negatives(cfg, alias, pos, slot, iteration)
     tok = tokens.astype(np.int64)
@@ -270,7 +271,8 @@ def sgns_minibatch_reference(syn0: torch.Tensor, syn1: torch.Tensor, cfg: SGNSCo
 
 
 def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, alpha, ci, cj, stats,
-                              row_scale0=None, row_scale1=None, tile_neg_scale: float = 1.0) -> StepStats:
+                              row_scale0=None, row_scale1=None, tile_neg_scale: float = 1.0,
+                              tile_neg_weight: float = 1.0) -> StepStats:
     """neg_sharing="tile": positives per pair, negatives per (active centre, shared negative of its tile) with
     weight m_i * n / N; every dot from pre-update rows, all updates summed."""
     tok = tokens.astype(np.int64)
@@ -289,7 +291,9 @@ def _minibatch_tile_reference(syn0, syn1, cfg, alias, tokens, pos0, iteration, a
     ua = syn0[wa]                                                           # [A, d]
     vn = syn1[ng]                                                           # [A, N, d]
     fminus = torch.einsum("ad,and->an", ua, vn)
-    gminus = sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * wgt[:, None]
+    # tile_neg_weight scales the negative term of the UPDATES on both sides (EngineOptions.tile_neg_weight); the loss
+    # keeps the full weight
+    gminus = sigmoid_coeff(fminus, 0.0, alpha, cfg.sigmoid_mode, cfg.max_grad) * (wgt * float(tile_neg_weight))[:, None]
     stats.loss = float(sgns_loss(fplus, fminus, wgt[:, None].expand_as(fminus)))
     stats.max_abs_dot = float(max(fplus.abs().max(), fminus.abs().max()))
     du_pos = gplus[:, None] * vc

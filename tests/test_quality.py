@@ -142,3 +142,19 @@ def test_estimator_passes_num_partitions_and_unigram_table_size_to_the_engine():
     assert o["num_partitions"] == 3 and o["unigram_table_size"] == 12345 and o["sampler"] == "table"
     eo = EngineOptions.from_dict(o)
     assert eo.num_partitions == 3 and eo.unigram_table_size == 12345 and eo.hot_row_cap == 8
+
+
+def test_staleness_window_rounding_is_tight_and_monotone():
+    """engine.round_window: never below the exact window, at most 12.5 % above it (a power-of-two rounding once cost
+    planted recall, profiles/r2_quality.md), monotone, and few distinct values."""
+    from glint_word2vec_b200.models.engine import round_window
+    prev = 0
+    seen = set()
+    for w in list(range(1, 5000)) + [18944, 131072, 131073, 10 ** 6]:
+        r = round_window(w)
+        assert w <= r <= w * 1.125 + 1e-9
+        assert r >= prev or w > 4999
+        prev = r if w < 5000 else prev
+        seen.add(r)
+    assert round_window(4096) == 4096 and round_window(585) == 640 and round_window(18944) == 20480
+    assert len({round_window(w) for w in range(2048, 4097)}) <= 9
