@@ -146,3 +146,28 @@ def test_failure_on_one_rank_fails_the_request_everywhere_and_the_group_survives
         assert h2.norms().shape == (30,)
     finally:
         _stop(proc, port, secret)
+
+
+def test_fit_text_file_streams_the_corpus_to_a_server_group(tmp_path):
+    """fitTextFile in integrated server mode: the encoded corpus is streamed to disk and the two shard servers receive
+    its PREFIX (nothing is pickled, no rank holds a private copy); the model equals the single-process one."""
+    import numpy as np
+    from glint_word2vec_b200 import ServerSideGlintWord2Vec
+    from glint_word2vec_b200.data.synthetic import synthetic_capitals_corpus
+    sentences = synthetic_capitals_corpus(seed=3)[:1200]
+    path = tmp_path / "corpus.txt"
+    path.write_text("\n".join(" ".join(s) for s in sentences), encoding="utf-8")
+    kw = dict(inputCol="s", outputCol="v", vectorSize=16, minCount=2, seed=5)
+    m1 = ServerSideGlintWord2Vec(numParameterServers=1, parameterServerConfig={"device": "cpu"}, **kw).fitTextFile(str(path))
+    m2 = ServerSideGlintWord2Vec(numParameterServers=2,
+                                 parameterServerConfig={"device": "cpu", "stream_threshold_bytes": 0,
+                                                        "scratch_dir": str(tmp_path)}, **kw).fitTextFile(str(path))
+    try:
+        assert m2._require_handle().num_shards == 2
+        v1, v2 = m1.getVectorsMap(), m2.getVectorsMap()
+        assert v1.keys() == v2.keys()
+        assert all(np.allclose(v1[w], v2[w], atol=1e-5) for w in list(v1)[:80])
+        assert not [p for p in tmp_path.iterdir() if p.name.startswith("gw2v-corpus-")]      # the temporary stream is gone
+    finally:
+        m1.stop()
+        m2.stop()
